@@ -1,0 +1,216 @@
+/*
+ * rtc.h -- C-ABI of the B200-native console ray tracer hot path ("rtc").
+ *
+ * This is the drop-in boundary for ONE path of EmilHogstedt/Raytracing-in-Windows-Console:
+ * everything inside RayTracingManager::Update (reference RayTracingManager.cu:76-154):
+ * camera ray generation -> nearest-hit ray/sphere + ray/plane -> Blinn-Phong shading ->
+ * integer quantisation -> ANSI escape stream (the bytes handed to
+ * PrintMachine::SetDataInBackBuffer, reference PrintMachine.cpp:178-192).
+ *
+ * The reference has no FFI; the seam is a C++ call.  The C++ facade classes in
+ * raytracing-in-windows-console_b200/host/ keep the reference's class names and signatures
+ * (Engine3D / Scene3D / Object3D / Sphere / Plane / Camera3D / RayTracingManager /
+ * PrintMachine) and forward to the entry points below.  Each entry point cites the
+ * reference interface it replaces.
+ *
+ * Conventions
+ *   - plain C types only (pointers, sizes, PODs); no C++/torch types cross this boundary;
+ *   - every function returns 0 on success and a negative rtc_status on failure; the
+ *     message is available from rtc_last_error() (thread-local).  Nothing here calls
+ *     exit() (the reference's gpuErrchk does, pch.h:45-53) and nothing throws;
+ *   - one context = one GPU = one caller thread (the reference is single-threaded on
+ *     this path); multi-GPU = one context (and normally one process) per GPU,
+ *     each tracing a row band (rtc_trace_band), gathered by the caller;
+ *   - there is NO CPU fallback: with no usable CUDA device rtc_create fails with
+ *     RTC_ERR_CUDA.
+ *   - "x" is the console width INCLUDING the newline column, exactly as in the reference:
+ *     traced cells per row = x-1 (RayTracing.cu:491), rays per frame = (x-1)*y.
+ */
+#ifndef RTC_H_
+#define RTC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define RTC_API __attribute__((visibility("default")))
+#else
+#define RTC_API
+#endif
+
+typedef struct rtc_ctx rtc_ctx;
+
+typedef enum rtc_status {
+    RTC_OK = 0,
+    RTC_ERR_INVALID = -1, /* bad argument / bad state                                  */
+    RTC_ERR_CUDA = -2,    /* a CUDA runtime call failed (message has the CUDA string)   */
+    RTC_ERR_NOMEM = -3,   /* host or device allocation failed                           */
+    RTC_ERR_CAPACITY = -4 /* scene/output capacity exceeded                             */
+} rtc_status;
+
+/* == RenderingMode, same order (reference RayTracingManager.h:21). */
+typedef enum rtc_mode {
+    RTC_BIT_ASCII = 0,   /* ESC[38;5;Nm<ch>   12-byte cells, xterm-256 index           */
+    RTC_BIT_PIXEL = 1,   /* ESC[48;5;Nm<sp>                                            */
+    RTC_RGB_ASCII = 2,   /* ESC[38;2;R;G;Bm<ch> 20-byte cells                          */
+    RTC_RGB_PIXEL = 3,   /* ESC[48;2;R;G;Bm<sp>                                        */
+    RTC_RGB_NORMALS = 4, /* as RGB_PIXEL with colour = (uint8)(normal*255)             */
+    RTC_SDL = 5          /* reference stub: traces, writes nothing (RayTracing.cu:755) */
+} rtc_mode;
+
+/* == ObjectType (reference Object3D.h:14). */
+enum { RTC_OBJ_NONE = 0, RTC_OBJ_PLANE = 1, RTC_OBJ_SPHERE = 2 };
+
+/* Flags for rtc_render / rtc_trace_band / rtc_update_objects. */
+enum {
+    RTC_FLAG_NONE = 0u,
+    /* Extension (NOT in the reference, which casts no shadow rays -- SURVEY F1): any-hit
+     * query from the shaded point toward the light (1,50,0); occluded pixels keep only the
+     * ambient term.  Off by default; all parity claims are made with it off.            */
+    RTC_FLAG_SHADOWS = 1u << 0,
+    /* rtc_update_objects: mirror the reference's launch bug -- its UpdateObjects launch
+     * uses block = count threads, which CUDA rejects when count > 1024, so no object moves
+     * (RayTracingManager.cu:89-107).  Without this flag all objects are updated.        */
+    RTC_FLAG_UPDATE_REF_LAUNCH_LIMIT = 1u << 1
+};
+
+/* == RayTracingCPUToGPUData (reference RayTracingManager.h:9-19) without the vptrs.
+ * inv_view is row-major: inv_view[4*r + c] = Matrix::row{r+1}.{x,y,z,w}[c].            */
+typedef struct rtc_params {
+    float inv_view[16];
+    float cam_pos[3];
+    uint32_t x;       /* console width incl. newline column  (PrintMachine::GetWidth)  */
+    uint32_t y;       /* console height                      (PrintMachine::GetHeight) */
+    float element1;   /* projection [0][0] (Engine3D.cpp:94)                           */
+    float element2;   /* projection [1][1] (Engine3D.cpp:95)                           */
+    float cam_far;    /* far-plane distance (Engine3D.cpp:96)                          */
+} rtc_params;
+
+/* One scene object, 64 bytes.  The union of the reference's Sphere (Sphere.h:5-25) and
+ * Plane (Plane.h:5-38) state; colour is float 0..255 per channel as in the reference.  */
+typedef struct rtc_object {
+    int32_t type;      /* RTC_OBJ_SPHERE / RTC_OBJ_PLANE                                 */
+    float center[3];   /* Object3D::m_center                                             */
+    float color[3];    /* Object3D::m_color                                              */
+    float radius;      /* Sphere::m_radius                                               */
+    float normal[3];   /* Plane::m_normal -- stored ALREADY normalised (Plane.cu:9)       */
+    float width;       /* Plane::m_width  (extent along world X)                          */
+    float height;      /* Plane::m_height (extent along world Z)                          */
+    float speed;       /* Sphere::speed                                                  */
+    int32_t mover;     /* Sphere::mover (+1/-1)                                          */
+    int32_t reserved_;
+} rtc_object;
+
+/* Per-stage device timings of the last rtc_render on this context (CUDA events). */
+typedef struct rtc_timings {
+    float prep_ms;    /* per-frame scene hoist (oc, c per sphere)          */
+    float trace_ms;   /* kernel 1: ray generation + nearest hit            */
+    float shade_ms;   /* kernel 2: shade + quantise                        */
+    float encode_ms;  /* kernel 3: ANSI encode (scan + scatter)            */
+    float total_ms;   /* first launch to last kernel end                   */
+    uint32_t launches;/* kernels launched by the last rtc_render           */
+} rtc_timings;
+
+/* ---- context ------------------------------------------------------------------------ */
+/* Replaces RayTracingManager::RayTracingManager (RayTracingManager.cu:53-67) + the device
+ * side of Scene3D::Init (Scene3D.cpp:7-26).  `device` is a CUDA ordinal.                */
+RTC_API int rtc_create(rtc_ctx** out, int device);
+/* Replaces ~RayTracingManager (RayTracingManager.cu:69-74) + Scene3D::CleanUp (:94-99). */
+RTC_API void rtc_destroy(rtc_ctx* ctx);
+RTC_API const char* rtc_last_error(void);
+RTC_API const char* rtc_version(void);
+/* Run all work of this context on an externally owned cudaStream_t (e.g. torch's current
+ * stream), or pass NULL to go back to the context's own stream.                         */
+RTC_API int rtc_set_stream(rtc_ctx* ctx, void* cuda_stream);
+RTC_API int rtc_device_info(rtc_ctx* ctx, int* sm_count, int* clock_khz, size_t* smem_optin);
+
+/* ---- sink geometry: PrintMachine::Start / ChangeSize (PrintMachine.cpp:108-152,:216) - */
+RTC_API int rtc_resize(rtc_ctx* ctx, uint32_t x, uint32_t y);
+
+/* ---- scene: Scene3D (Scene3D.cpp:36-105) ---------------------------------------------- */
+RTC_API int rtc_scene_clear(rtc_ctx* ctx);
+/* Scene3D::CreateSphere (Scene3D.cpp:36-60).  speed/mover: the reference draws speed from
+ * host rand() (Sphere.cu:11-12) and starts mover at -1; here they are explicit.          */
+RTC_API int rtc_scene_add_sphere(rtc_ctx* ctx, const float center[3], float radius,
+                                 const float rgb[3], float speed, int mover);
+/* Scene3D::CreatePlane (Scene3D.cpp:62-86); `normal` is normalised here like Plane.cu:9. */
+RTC_API int rtc_scene_add_plane(rtc_ctx* ctx, const float center[3], const float normal[3],
+                                const float rgb[3], float width, float height);
+/* Bulk replace (objects taken verbatim, plane normals must already be normalised).       */
+RTC_API int rtc_scene_set_objects(rtc_ctx* ctx, const rtc_object* objs, uint32_t n);
+/* Scene3D::GetObjects (Scene3D.cpp:102-105) -- host copy of the current object state
+ * (after any rtc_update_objects).                                                        */
+RTC_API int rtc_scene_get_objects(rtc_ctx* ctx, rtc_object* out, uint32_t cap, uint32_t* n);
+RTC_API int rtc_scene_count(rtc_ctx* ctx, uint32_t* n);
+/* UpdateObjects kernel / Sphere::Update (RayTracingManager.cu:10-44, Sphere.cu:15-23).   */
+RTC_API int rtc_update_objects(rtc_ctx* ctx, double dt, uint32_t flags);
+
+/* ---- frame: RayTracingManager::Update (RayTracingManager.cu:76-154) -------------------- */
+/* Asynchronous: enqueue hoist + trace + shade/quantise + ANSI encode for the whole frame
+ * on the context's stream (replaces :83-127 and the host minimiser :146).                */
+RTC_API int rtc_render(rtc_ctx* ctx, const rtc_params* params, rtc_mode mode, uint32_t flags);
+/* Synchronise and return the minimised ANSI stream in a pinned host buffer owned by the
+ * context (valid until the next rtc_render).  These are exactly the `size` bytes the
+ * reference passes to PrintMachine::SetDataInBackBuffer (RayTracingManager.cu:150).      */
+RTC_API int rtc_frame_ansi(rtc_ctx* ctx, const char** host_ptr, size_t* n_bytes);
+/* Headless: the stream stays in HBM.  Synchronises only to learn n_bytes.                */
+RTC_API int rtc_frame_ansi_device(rtc_ctx* ctx, const char** dev_ptr, size_t* n_bytes);
+/* Parity hooks: quantised colour plane ((x-1)*y*bpp bytes, bpp = 3 for the RGB modes, 1 =
+ * xterm-256 index for the 8-bit modes), glyph plane ((x-1)*y bytes, ' ' on a miss; NULL in
+ * the PIXEL/NORMALS modes) and hit records (distance; object index or -1) of the last
+ * rtc_render, copied to host buffers owned by the context.                               */
+RTC_API int rtc_frame_color(rtc_ctx* ctx, const uint8_t** host_color, uint32_t* bpp,
+                            const uint8_t** host_glyph);
+RTC_API int rtc_frame_hits(rtc_ctx* ctx, const float** host_dist, const int32_t** host_index);
+/* RayTracingManager::Update as one synchronous call: optional physics step (dt != 0),
+ * render, copy the stream to host.                                                        */
+RTC_API int rtc_update(rtc_ctx* ctx, const rtc_params* params, rtc_mode mode, double dt,
+                       uint32_t flags, const char** host_ptr, size_t* n_bytes);
+RTC_API int rtc_last_timings(rtc_ctx* ctx, rtc_timings* out);
+
+/* ---- stage-level entry points on caller-owned DEVICE buffers ---------------------------
+ * (used for multi-GPU row bands and for the encode-only workload; all asynchronous on the
+ * context's stream).                                                                      */
+/* RayTracing::RayTrace (RayTracing.h:31-38, RayTracing.cu:797-867) restricted to rows
+ * [row0,row1): writes (row1-row0)*(x-1)*bpp colour bytes to dev_color and, in the ASCII
+ * modes, (row1-row0)*(x-1) glyph bytes to dev_glyph (may be NULL otherwise).  The pointers
+ * may be peer-mapped memory of another GPU.                                               */
+RTC_API int rtc_trace_band(rtc_ctx* ctx, const rtc_params* params, rtc_mode mode,
+                           uint32_t flags, uint32_t row0, uint32_t row1,
+                           uint8_t* dev_color, uint8_t* dev_glyph);
+/* MinimizeRGB / Minimize8bit (RayTracingManager.cu:251-319 / :181-249) on the device:
+ * colour plane (+glyph plane) of an x-by-y frame -> minimised stream in dev_out (capacity
+ * cap bytes; rtc_encode_capacity gives the worst case).  *dev_total (8-byte device or
+ * mapped-host location) receives the stream length.                                       */
+RTC_API int rtc_encode(rtc_ctx* ctx, const uint8_t* dev_color, const uint8_t* dev_glyph,
+                       uint32_t x, uint32_t y, rtc_mode mode, char* dev_out, size_t cap,
+                       unsigned long long* dev_total);
+RTC_API size_t rtc_encode_capacity(uint32_t x, uint32_t y, rtc_mode mode);
+RTC_API uint32_t rtc_mode_bpp(rtc_mode mode);
+RTC_API uint32_t rtc_mode_has_glyph(rtc_mode mode);
+
+/* CUDA IPC plumbing so that rank g can write its band straight into rank 0's frame buffer
+ * over NVLink (the gather fused into the shade kernel's stores).                          */
+RTC_API int rtc_ipc_export(rtc_ctx* ctx, void* dev_ptr, unsigned char handle_out[64]);
+RTC_API int rtc_ipc_open(rtc_ctx* ctx, const unsigned char handle[64], void** dev_ptr);
+RTC_API int rtc_ipc_close(rtc_ctx* ctx, void* dev_ptr);
+
+/* ---- host-side helpers that need no GPU (reference host code on the path) -------------- */
+/* Camera3D::Init + Update + GetInverseVMatrix + Engine3D::Render's parameter block
+ * (Camera3D.cpp:8-48, :51-98, :207-376; Engine3D.cpp:88-97).  pixel_aspect is the
+ * reference's hard-coded 0.01f (Camera3D.cpp:17); pass 0 for that default.               */
+RTC_API int rtc_camera_params(uint32_t x, uint32_t y, const float pos[3], const float rot[3],
+                              float pixel_aspect, rtc_params* out);
+
+/* ---- microbenchmark: FP32 pipe peak measured on this GPU (roofline denominator) -------- */
+/* variant 0: scalar FFMA chain, 1: packed FFMA2 chain.  Returns achieved TFLOP/s.          */
+RTC_API int rtc_fp32_peak(rtc_ctx* ctx, int variant, int iters, float* tflops, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTC_H_ */
