@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native console ray tracer hot path.
+
+Metric (BASELINE.json): Mrays/s (and frames/s) at 3840x2160, 1024 random spheres + plane,
+RGB_PIXEL mode, on 1/2/4/8 B200 with a row-band split gathered to GPU 0; ray-kernel fraction of
+the FP32 roofline; encoder fraction of HBM bandwidth.
+
+A "step" is one whole frame of the hot path: scene hoist -> ray kernel -> shade+quantise ->
+(N>1: gather of the RGB8 bands to GPU 0) -> ANSI encode.  `value` is timed on the device with
+CUDA events (inputs resident in HBM); `e2e` is the same frame through the C-ABI with HOST
+buffers: scene + camera block uploaded, minimised stream copied back to pinned host memory.
+
+  python bench.py --gpus 1 --steps 20 --warmup 5
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...     # the reference's own CPU code on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config3_4k_1024")
+    ap.add_argument("--mode", default="RGB_PIXEL")
+    ap.add_argument("--gather", default="nccl", choices=["nccl", "ipc"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm_gbs=float(d.get("hbm_gbs", 6650.0)), sm_max_mhz=float(d.get("sm_max_mhz", 1965.0)), source="measured")
+    return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._th = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for nm, v in zip(names, out[2:6]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        self._th = threading.Thread(target=self._run, daemon=True)
+        self._th.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._th:
+            self._th.join(timeout=6)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def band(y, rank, world):
+    return (y * rank) // world, (y * (rank + 1)) // world
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_sample(name, mode, seconds, threads=None):
+    """Time the reference's own CPU code (oracle/_ref, built from the unmodified sources) on a
+    bounded sample of the workload: a window of 16-row block rows of the frame, all host threads.
+    Falls back to the restated oracle (kind 'port') where oracle/_ref is absent."""
+    from oracle.oracle import Oracle, Reference
+    from rtc_b200 import scenes
+    objs = scenes.config_scene(name)
+    p = scenes.config_camera(name)
+    threads = threads or os.cpu_count() or 1
+    n_obj = len(objs)
+    gy = (p.y + 15) // 16
+    mid = gy // 2
+    if Reference.available():
+        R = Reference()
+        kind = "reference"
+
+        def run(b0, b1):
+            return R.trace_blockrows(objs, p, mode, b0, b1, threads)
+    else:
+        O = Oracle()
+        kind = "port"
+
+        def run(b0, b1):
+            r0, r1 = b0 * 16, min(b1 * 16, p.y)
+            return O.time_trace(objs, p, mode, r0, r1, threads), (r1 - r0) * (p.x - 1)
+    # calibrate on a thin window through the middle of the frame, then size the sample
+    nb = max(1, min(gy, (threads + 239) // 240))
+    secs, rays = run(mid, mid + nb)
+    rate = rays / max(secs, 1e-9)
+    want_rays = rate * seconds
+    rows_per_block = 16 * (p.x - 1)
+    nblocks = int(max(nb, min(gy, round(want_rays / rows_per_block))))
+    b0 = max(0, mid - nblocks // 2)
+    b1 = min(gy, b0 + nblocks)
+    secs, rays = run(b0, b1)
+    return dict(kind=kind, cores=threads, secs=secs, rays=rays, mrays_s=rays / secs / 1e6,
+                sample="%d of %d rows (block rows %d..%d through the frame centre) of %s, %d objects, %s kernel only"
+                       % (min(b1 * 16, p.y) - b0 * 16, p.y, b0, b1, name, n_obj, "reference RayTrace_*" if kind == "reference" else "oracle"))
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import rtc_b200
+    mode = rtc_b200.MODE_NAMES.index(args.mode)
+    from rtc_b200 import scenes
+    p = scenes.config_camera(args.workload)
+    per_step = max(1.0, min(args.cpu_seconds, 150.0 / max(1, args.steps + args.warmup)))
+    vals = []
+    last = None
+    for i in range(args.warmup + args.steps):
+        last = cpu_reference_sample(args.workload, mode, per_step)
+        if i >= args.warmup:
+            vals.append(last)
+    rays = sum(v["rays"] for v in vals)
+    secs = sum(v["secs"] for v in vals)
+    value = rays / secs / 1e6
+    frame_rays = (p.x - 1) * p.y
+    line = {
+        "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * frame_rays / (value * 1e6),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "mode": args.mode, "note": "ms_per_step = whole-frame time extrapolated from the sample rate"},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "frames_per_s": value * 1e6 / frame_rays,
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import rtc_b200
+    from rtc_b200 import scenes
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    mode = rtc_b200.MODE_NAMES.index(args.mode)
+    name = args.workload
+    objs = scenes.config_scene(name)
+    p = scenes.config_camera(name)
+    x, y = p.x, p.y
+    W = x - 1
+    bpp = rtc_b200.mode_bpp(mode)
+    has_glyph = rtc_b200.mode_has_glyph(mode)
+    n_spheres = int((objs["type"] == 2).sum())
+    frame_rays = W * y
+
+    ctx = rtc_b200.Context(local_rank)            # raises without a GPU: no CPU fallback
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_objects(objs)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")      # > 126 MB L2
+
+    r0, r1 = band(y, rank, world)
+    cap = rtc_b200.encode_capacity(x, y, mode)
+    launches_per_step = 0
+    if world == 1:
+        def step():
+            ctx.render(p, mode)
+    else:
+        # row bands: every rank traces + shades its band; bands are gathered into rank 0's frame
+        # buffer (NCCL send/recv, or written straight into it over NVLink through a CUDA-IPC mapping);
+        # rank 0 encodes the assembled frame.
+        frame_color = torch.empty(W * y * bpp + 16, dtype=torch.uint8, device="cuda") if rank == 0 else None
+        frame_glyph = torch.empty(W * y + 16, dtype=torch.uint8, device="cuda") if (rank == 0 and has_glyph) else None
+        band_color = torch.empty(max(1, (r1 - r0) * W * bpp), dtype=torch.uint8, device="cuda")
+        band_glyph = torch.empty(max(1, (r1 - r0) * W), dtype=torch.uint8, device="cuda") if has_glyph else None
+        out = torch.empty(cap, dtype=torch.uint8, device="cuda") if rank == 0 else None
+        total = torch.zeros(1, dtype=torch.int64, device="cuda") if rank == 0 else None
+        bands = [band(y, g, world) for g in range(world)]
+        peer_color = peer_glyph = 0
+        if args.gather == "ipc":
+            handles = [None, None]
+            if rank == 0:
+                handles = [ctx.ipc_export(frame_color.data_ptr()), ctx.ipc_export(frame_glyph.data_ptr()) if has_glyph else None]
+            dist.broadcast_object_list(handles, src=0)
+            if rank != 0:
+                peer_color = ctx.ipc_open(handles[0])
+                peer_glyph = ctx.ipc_open(handles[1]) if has_glyph else 0
+            else:
+                peer_color = frame_color.data_ptr()
+                peer_glyph = frame_glyph.data_ptr() if has_glyph else 0
+
+        def step():
+            if args.gather == "ipc":
+                ctx.trace_band(p, mode, r0, r1, peer_color + r0 * W * bpp, (peer_glyph + r0 * W) if has_glyph else 0)
+                dist.barrier()                     # stream-ordered: all bands have landed in GPU 0's HBM
+            else:
+                dst_c = frame_color[r0 * W * bpp:r1 * W * bpp] if rank == 0 else band_color
+                dst_g = (frame_glyph[r0 * W:r1 * W] if rank == 0 else band_glyph) if has_glyph else None
+                ctx.trace_band(p, mode, r0, r1, dst_c.data_ptr(), dst_g.data_ptr() if has_glyph else 0)
+                ops = []
+                if rank == 0:
+                    for g in range(1, world):
+                        a, b = bands[g]
+                        ops.append(dist.P2POp(dist.irecv, frame_color[a * W * bpp:b * W * bpp], g))
+                        if has_glyph:
+                            ops.append(dist.P2POp(dist.irecv, frame_glyph[a * W:b * W], g))
+                else:
+                    ops.append(dist.P2POp(dist.isend, band_color, 0))
+                    if has_glyph:
+                        ops.append(dist.P2POp(dist.isend, band_glyph, 0))
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+            if rank == 0:
+                ctx.encode(frame_color.data_ptr(), frame_glyph.data_ptr() if has_glyph else 0, x, y, mode,
+                           out.data_ptr(), cap, total.data_ptr())
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-timed throughput ---------------------------------------------------------------
+    for _ in range(max(3, args.warmup)):
+        step()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    stage = {"prep_ms": 0.0, "trace_ms": 0.0, "shade_ms": 0.0, "encode_ms": 0.0}
+    sync_all()
+    for i in range(args.steps):
+        flush.zero_()                              # evict L2 between timed iterations (untimed)
+        ev[i][0].record(stream)
+        step()
+        ev[i][1].record(stream)
+        if world == 1:
+            torch.cuda.synchronize()
+            t = ctx.timings()
+            for k in stage:
+                stage[k] += t[k]
+            launches_per_step = t["launches"]
+    sync_all()
+    clocks = sampler.stop() if rank == 0 else None
+    my_ms = sum(a.elapsed_time(b) for a, b in ev)
+    if dist is not None:
+        tt = torch.tensor([my_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    else:
+        total_ms = my_ms
+    ms_per_step = total_ms / args.steps
+    value = frame_rays / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end to end through the C-ABI with host buffers (N == 1 path; N > 1: rank 0 reads the stream back)
+    e2e = None
+    if world == 1:
+        for _ in range(2):
+            ctx.set_objects(objs)
+            s = ctx.update(p, mode, dt=0.0, flags=rtc_b200.FLAG_UPDATE_REF_LAUNCH_LIMIT)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        nbytes = 0
+        for _ in range(args.steps):
+            ctx.set_objects(objs)                  # scene + camera block from host memory every frame
+            s = ctx.update(p, mode, dt=0.0, flags=rtc_b200.FLAG_UPDATE_REF_LAUNCH_LIMIT)   # stream lands in pinned host memory
+            nbytes = len(s)
+        t1 = time.perf_counter()
+        e2e_ms = (t1 - t0) * 1e3 / args.steps
+        e2e = {"value": frame_rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": int(objs.nbytes + 96), "d2h_bytes_per_step": int(nbytes + 8),
+               "api": "rtc_scene_set_objects + rtc_update (== RayTracingManager::Update), stream returned in pinned host memory"}
+    else:
+        host = torch.empty(cap, dtype=torch.uint8, pin_memory=True) if rank == 0 else None
+        sync_all()
+        t0 = time.perf_counter()
+        nbytes = 0
+        for _ in range(args.steps):
+            ctx.set_objects(objs)
+            step()
+            if rank == 0:
+                n = int(total.item())              # D2H of the length (syncs the stream)
+                host[:n].copy_(out[:n], non_blocking=True)
+                torch.cuda.synchronize()
+                nbytes = n
+        sync_all()
+        t1 = time.perf_counter()
+        tt = torch.tensor([(t1 - t0) * 1e3 / args.steps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tt.item())
+        e2e = {"value": frame_rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": int(objs.nbytes + 96) * world, "d2h_bytes_per_step": int(nbytes + 8),
+               "api": "rtc_scene_set_objects + rtc_trace_band per rank, gather to GPU 0, rtc_encode, stream copied to pinned host memory"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    sm_count = ctx.device_info()["sm_count"]
+    fp32_peak = sm_count * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12          # TFLOP/s at the max SM clock
+    line = {
+        "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": name, "x": x, "y": y, "rays_per_frame": frame_rays, "spheres": n_spheres,
+                   "objects": int(len(objs)), "mode": args.mode, "parallelism": "rowband%d" % world,
+                   "gather": args.gather if world > 1 else None, "l2": "flushed between timed steps (256 MiB memset, untimed)"},
+        "frames_per_s": 1e3 / ms_per_step,
+        "clocks": clocks, "e2e": e2e,
+    }
+    if world == 1:
+        trace_ms = stage["trace_ms"] / args.steps
+        enc_ms = stage["encode_ms"] / args.steps
+        achieved = 7.0 * frame_rays * n_spheres / (trace_ms * 1e-3) / 1e12
+        try:
+            measured_ffma = max(ctx.fp32_peak(0, 3000)[0] for _ in range(2))
+            measured_ffma2 = max(ctx.fp32_peak(1, 3000)[0] for _ in range(2))
+        except Exception:
+            measured_ffma = measured_ffma2 = None
+        _, n_stream = ctx.frame_ansi_device()
+        line["roofline"] = {"bound": "fp32", "kernel": "trace_kernel", "achieved": achieved, "peak": fp32_peak,
+                            "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": None,
+                            "peak_source": "%d SMs x 128 lanes x 2 FLOP x %.0f MHz (%s sm_max_mhz); not in MEASURED_PEAKS.json, which has HBM and bf16 tensor only"
+                                           % (sm_count, pk["sm_max_mhz"], pk["source"]),
+                            "algorithmic_flops_per_launch": 7.0 * frame_rays * n_spheres, "kernel_ms": trace_ms,
+                            "measured_ffma_tflops": measured_ffma, "measured_ffma2_tflops": measured_ffma2,
+                            "frac_of_measured_ffma": (achieved / measured_ffma) if measured_ffma else None}
+        enc_bytes = bpp * frame_rays + n_stream
+        line["roofline_encoder"] = {"bound": "hbm", "kernel": "encode_kernel", "achieved": enc_bytes / (enc_ms * 1e-3) / 1e9,
+                                    "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": enc_bytes / (enc_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                                    "traffic": None, "algorithmic_bytes_per_launch": enc_bytes, "kernel_ms": enc_ms,
+                                    "peak_source": pk["source"]}
+        line["stages_ms"] = {k: v / args.steps for k, v in stage.items()}
+        line["gpu_launches"] = int(launches_per_step * args.steps)
+        if not args.no_cpu_baseline:
+            try:
+                cb = cpu_reference_sample(name, mode, args.cpu_seconds)
+                line["cpu_baseline"] = {"value": cb["mrays_s"], "unit": "Mrays/s", "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]}
+            except Exception as e:  # the checker being absent must not hide the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
+    else:
+        # hoist + trace + shade per rank, + encode on rank 0
+        line["gpu_launches"] = int((3 * world + 1) * args.steps)
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

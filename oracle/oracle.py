@@ -10,7 +10,6 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl refere
 import this module.
 """
 import ctypes
-import importlib.util
 import os
 import subprocess
 import sys
@@ -21,20 +20,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 
 
-def _load_pkg():
-    name = "rtc_b200"
-    if name in sys.modules:
-        return sys.modules[name]
-    pkg_dir = os.path.join(_ROOT, "raytracing-in-windows-console_b200")
-    spec = importlib.util.spec_from_file_location(
-        name, os.path.join(pkg_dir, "__init__.py"), submodule_search_locations=[pkg_dir])
-    mod = importlib.util.module_from_spec(spec)
-    sys.modules[name] = mod
-    spec.loader.exec_module(mod)
-    return mod
-
-
-_pkg = _load_pkg()
+sys.path.insert(0, _ROOT) if _ROOT not in sys.path else None
+import rtc_b200  # noqa: E402,F401  (root-level import shim for the hyphenated package directory)
 from rtc_b200._types import (OBJECT_DTYPE, RtcParams, mode_bpp, mode_cell,  # noqa: E402
                              mode_has_glyph, obj_ptr)
 

@@ -1,0 +1,42 @@
+"""Build librtc_b200.so (CUDA kernels + C-ABI) in-tree with nvcc for sm_100a."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+SOURCES = ["rtc_api.cu", "rtc_trace.cu", "rtc_shade.cu", "rtc_encode.cu", "rtc_microbench.cu", "rtc_camera.cpp"]
+LIB = os.path.join(HERE, "librtc_b200.so")
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "--fmad=false",                      # exact sections must not be contracted; fused ops are explicit
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden,-Wall",
+    "-cudart", "static", "-shared",
+]
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "rtc.h"), __file__]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed building librtc_b200.so")
+    if verbose:
+        sys.stderr.write(r.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force=True, verbose="-v" in sys.argv)
+    print(LIB)

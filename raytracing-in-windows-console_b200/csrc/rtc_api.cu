@@ -1,0 +1,621 @@
+// rtc_api.cu -- the C-ABI of include/rtc.h: context, scene store, frame driver.
+//
+// Replaces the host side of RayTracingManager (reference RayTracingManager.cu:53-165) and the
+// device-array bookkeeping of Scene3D (Scene3D.cpp:7-164).  Differences by design:
+//   * the scene lives in ONE device array of 64-byte PODs uploaded in a single async copy
+//     when dirty (the reference issues 2 blocking cudaMemcpy per object, Scene3D.cpp:47-59);
+//   * nothing is memset per frame (the reference clears 20*x*y bytes, :161-165) because the
+//     20-byte raw cell buffer does not exist;
+//   * only the minimised stream crosses PCIe (the reference copies the whole raw buffer to
+//     pageable memory, :143, then minimises on one host thread, :146);
+//   * errors are returned, never exit()ed (pch.h:45-53).
+// There is no CPU fallback anywhere in this file: without a CUDA device rtc_create fails.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "rtc_device.cuh"
+#include "rtc_kernels.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(RTC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+inline bool mode_is_8bit(int m) { return m == RTC_BIT_ASCII || m == RTC_BIT_PIXEL; }
+inline bool mode_has_glyph(int m) { return m == RTC_BIT_ASCII || m == RTC_RGB_ASCII; }
+inline uint32_t mode_bpp(int m) { return mode_is_8bit(m) ? 1u : 3u; }
+inline uint32_t mode_cell(int m) { return mode_is_8bit(m) ? 12u : 20u; }
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;   // elements
+    cudaError_t ensure(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+template <class T>
+struct PinBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMallocHost(&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct rtc_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int clock_khz = 0;
+    size_t smem_optin = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    uint32_t x = 0, y = 0;
+
+    // scene (host master copy + device mirror)
+    std::vector<rtc_object> objs;
+    std::vector<int32_t> sphere_obj, plane_obj;
+    bool scene_dirty = true;       // host -> device upload pending
+    bool host_stale = false;       // device physics ran; host copy must be refreshed before use
+    DevBuf<rtc_object> d_objs;
+    DevBuf<int32_t> d_sphere_obj, d_plane_obj;
+    DevBuf<float4> d_pairs;
+    DevBuf<float> d_c;
+
+    // frame buffers
+    DevBuf<float> d_hit_t;
+    DevBuf<int32_t> d_hit_idx;
+    DevBuf<uint8_t> d_color, d_glyph;
+    DevBuf<char> d_out;
+    DevBuf<unsigned long long> d_desc;
+    DevBuf<unsigned int> d_counters;        // [0..31] trace tile tickets, [32] encode ticket (never reset)
+    DevBuf<unsigned long long> d_total;
+    DevBuf<float> d_sink;
+    PinBuf<unsigned long long> h_total;
+    PinBuf<char> h_out;
+    PinBuf<uint8_t> h_color, h_glyph;
+    PinBuf<float> h_hit_t;
+    PinBuf<int32_t> h_hit_idx;
+    unsigned int enc_ticket_base = 0, enc_epoch = 0;
+
+    // last frame
+    bool have_frame = false;
+    int last_mode = RTC_RGB_PIXEL;
+    uint32_t last_x = 0, last_y = 0;
+    size_t last_cap = 0;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool timings_valid = false;
+    uint32_t last_launches = 0;
+};
+
+namespace {
+
+int upload_scene(rtc_ctx* c)
+{
+    if (!c->scene_dirty) return RTC_OK;
+    const size_t n = c->objs.size();
+    c->sphere_obj.clear();
+    c->plane_obj.clear();
+    for (size_t i = 0; i < n; ++i) {
+        if (c->objs[i].type == RTC_OBJ_SPHERE) c->sphere_obj.push_back((int32_t)i);
+        else if (c->objs[i].type == RTC_OBJ_PLANE) c->plane_obj.push_back((int32_t)i);
+    }
+    const size_t n_slots = (c->sphere_obj.size() + 1) & ~(size_t)1;
+    CK(c->d_objs.ensure(n > 0 ? n : 1));
+    CK(c->d_sphere_obj.ensure(n_slots > 0 ? n_slots : 2));
+    CK(c->d_plane_obj.ensure(c->plane_obj.size() > 0 ? c->plane_obj.size() : 1));
+    CK(c->d_pairs.ensure(n_slots > 0 ? n_slots : 2));
+    CK(c->d_c.ensure(n_slots > 0 ? n_slots : 2));
+    // Pageable sources: cudaMemcpyAsync stages them before returning, so the vectors may change afterwards.
+    if (n) CK(cudaMemcpyAsync(c->d_objs.p, c->objs.data(), n * sizeof(rtc_object), cudaMemcpyHostToDevice, c->stream));
+    if (!c->sphere_obj.empty())
+        CK(cudaMemcpyAsync(c->d_sphere_obj.p, c->sphere_obj.data(), c->sphere_obj.size() * sizeof(int32_t),
+                           cudaMemcpyHostToDevice, c->stream));
+    if (!c->plane_obj.empty())
+        CK(cudaMemcpyAsync(c->d_plane_obj.p, c->plane_obj.data(), c->plane_obj.size() * sizeof(int32_t),
+                           cudaMemcpyHostToDevice, c->stream));
+    c->scene_dirty = false;
+    return RTC_OK;
+}
+
+int refresh_host_scene(rtc_ctx* c)
+{
+    if (!c->host_stale) return RTC_OK;
+    if (!c->objs.empty()) {
+        CK(cudaMemcpyAsync(c->objs.data(), c->d_objs.p, c->objs.size() * sizeof(rtc_object), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    c->host_stale = false;
+    return RTC_OK;
+}
+
+rtc::FrameParams make_frame(const rtc_params* p, uint32_t row0, uint32_t row1)
+{
+    rtc::FrameParams f;
+    for (int i = 0; i < 12; ++i) f.m[i] = p->inv_view[i];
+    for (int i = 0; i < 3; ++i) f.cam[i] = p->cam_pos[i];
+    f.e1 = p->element1; f.e2 = p->element2; f.far_dist = p->cam_far;
+    f.fx = (float)p->x; f.fy = (float)p->y;     // size_t -> float in the reference (RayTracing.cu:16-17)
+    f.x = p->x; f.y = p->y; f.row0 = row0; f.row1 = row1;
+    return f;
+}
+
+// hoist + trace + shade for rows [row0,row1) into colour/glyph planes (band-relative).
+int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint32_t row0, uint32_t row1,
+                uint8_t* d_color, uint8_t* d_glyph, bool record_events)
+{
+    if (!p) return fail(RTC_ERR_INVALID, "params is NULL");
+    if (mode < RTC_BIT_ASCII || mode > RTC_SDL) return fail(RTC_ERR_INVALID, "invalid rendering mode %d", mode);
+    if (p->x < 1 || p->y < 1) return fail(RTC_ERR_INVALID, "invalid console size %ux%u", p->x, p->y);
+    if (row0 > row1 || row1 > p->y) return fail(RTC_ERR_INVALID, "invalid row band [%u,%u) of %u", row0, row1, p->y);
+    int rc = upload_scene(c);
+    if (rc) return rc;
+    const uint32_t W = p->x - 1u;
+    const size_t n_px = (size_t)(row1 - row0) * W;
+    const int n_spheres = (int)c->sphere_obj.size();
+    const int n_slots = (n_spheres + 1) & ~1;
+    const int n_planes = (int)c->plane_obj.size();
+    c->last_launches = 0;
+    if (record_events) CK(cudaEventRecord(c->ev[0], c->stream));
+    CK(rtc::launch_hoist(c->stream, c->d_objs.p, c->d_sphere_obj.p, n_spheres, n_slots, p->cam_pos, c->d_pairs.p,
+                         c->d_c.p, c->d_counters.p, 32));
+    c->last_launches++;
+    if (record_events) CK(cudaEventRecord(c->ev[1], c->stream));
+    if (n_px > 0) {
+        CK(c->d_hit_t.ensure(n_px));
+        CK(c->d_hit_idx.ensure(n_px));
+        const rtc::FrameParams fp = make_frame(p, row0, row1);
+        const int n_chunks = n_slots == 0 ? 1 : (n_slots + rtc::kMaxSlotsPerLaunch - 1) / rtc::kMaxSlotsPerLaunch;
+        if (n_chunks > 32) return fail(RTC_ERR_CAPACITY, "too many spheres (%d)", n_spheres);
+        for (int ch = 0; ch < n_chunks; ++ch) {
+            const int s0 = ch * rtc::kMaxSlotsPerLaunch;
+            const int slots = n_slots - s0 < rtc::kMaxSlotsPerLaunch ? n_slots - s0 : rtc::kMaxSlotsPerLaunch;
+            const int sph = n_spheres - s0 < slots ? n_spheres - s0 : slots;
+            const bool last = ch == n_chunks - 1;
+            CK(rtc::launch_trace(c->stream, c->sm_count, fp, c->d_pairs.p + s0, c->d_c.p + s0, c->d_sphere_obj.p + s0,
+                                 sph, slots, c->d_objs.p, c->d_plane_obj.p, last ? n_planes : 0, c->d_hit_t.p,
+                                 c->d_hit_idx.p, c->d_counters.p + ch, ch > 0 ? 1 : 0));
+            c->last_launches++;
+        }
+        if (record_events) CK(cudaEventRecord(c->ev[2], c->stream));
+        if (mode != RTC_SDL) {
+            CK(rtc::launch_shade(c->stream, fp, mode, flags, c->d_objs.p, (int)c->objs.size(), c->d_hit_t.p,
+                                 c->d_hit_idx.p, d_color, d_glyph));
+            c->last_launches++;
+        }
+        if (record_events) CK(cudaEventRecord(c->ev[3], c->stream));
+    } else if (record_events) {
+        CK(cudaEventRecord(c->ev[2], c->stream));
+        CK(cudaEventRecord(c->ev[3], c->stream));
+    }
+    return RTC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rtc_last_error(void) { return g_err; }
+const char* rtc_version(void) { return "rtc_b200 0.1 (sm_100a)"; }
+
+uint32_t rtc_mode_bpp(rtc_mode mode) { return mode_bpp(mode); }
+uint32_t rtc_mode_has_glyph(rtc_mode mode) { return mode_has_glyph(mode) ? 1u : 0u; }
+size_t rtc_encode_capacity(uint32_t x, uint32_t y, rtc_mode mode)
+{
+    if (x == 0) return 0;
+    return (size_t)(x - 1u) * y * mode_cell(mode) + y + 64;
+}
+
+int rtc_create(rtc_ctx** out, int device)
+{
+    if (!out) return fail(RTC_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(RTC_ERR_CUDA, "no usable CUDA device (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= n_dev) return fail(RTC_ERR_INVALID, "device %d out of range (0..%d)", device, n_dev - 1);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(RTC_ERR_CUDA, "device %d is sm_%d%d; this build targets sm_100a only", device, prop.major, prop.minor);
+    rtc_ctx* c = new (std::nothrow) rtc_ctx();
+    if (!c) return fail(RTC_ERR_NOMEM, "out of host memory");
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    cudaDeviceGetAttribute(&c->clock_khz, cudaDevAttrClockRate, device);
+#define CKC(call)                                                                                         \
+    do {                                                                                                  \
+        cudaError_t e2_ = (call);                                                                         \
+        if (e2_ != cudaSuccess) {                                                                         \
+            rtc_destroy(c);                                                                               \
+            return fail(RTC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e2_), __FILE__, __LINE__); \
+        }                                                                                                 \
+    } while (0)
+    CKC(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    for (auto& ev : c->ev) CKC(cudaEventCreate(&ev));
+    CKC(rtc::configure_trace());
+    CKC(rtc::configure_encode());
+    CKC(c->d_counters.ensure(rtc::kNumCounters));
+    CKC(cudaMemset(c->d_counters.p, 0, rtc::kNumCounters * sizeof(unsigned int)));
+    CKC(c->d_total.ensure(1));
+    CKC(c->d_sink.ensure(4));
+    CKC(c->h_total.ensure(1));
+#undef CKC
+    *out = c;
+    return RTC_OK;
+}
+
+void rtc_destroy(rtc_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+    c->d_objs.release(); c->d_sphere_obj.release(); c->d_plane_obj.release(); c->d_pairs.release(); c->d_c.release();
+    c->d_hit_t.release(); c->d_hit_idx.release(); c->d_color.release(); c->d_glyph.release(); c->d_out.release();
+    c->d_desc.release(); c->d_counters.release(); c->d_total.release(); c->d_sink.release();
+    c->h_total.release(); c->h_out.release(); c->h_color.release(); c->h_glyph.release();
+    c->h_hit_t.release(); c->h_hit_idx.release();
+    for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int rtc_set_stream(rtc_ctx* c, void* cuda_stream)
+{
+    if (!c) return fail(RTC_ERR_INVALID, "ctx is NULL");
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return RTC_OK;
+}
+
+int rtc_device_info(rtc_ctx* c, int* sm_count, int* clock_khz, size_t* smem_optin)
+{
+    if (!c) return fail(RTC_ERR_INVALID, "ctx is NULL");
+    if (sm_count) *sm_count = c->sm_count;
+    if (clock_khz) *clock_khz = c->clock_khz;
+    if (smem_optin) *smem_optin = c->smem_optin;
+    return RTC_OK;
+}
+
+int rtc_resize(rtc_ctx* c, uint32_t x, uint32_t y)
+{
+    if (!c) return fail(RTC_ERR_INVALID, "ctx is NULL");
+    if (x < 1 || y < 1) return fail(RTC_ERR_INVALID, "invalid console size %ux%u", x, y);
+    if ((uint64_t)(x - 1u) * y >= (1ull << 31)) return fail(RTC_ERR_CAPACITY, "console size %ux%u too large", x, y);
+    c->x = x; c->y = y;
+    return RTC_OK;
+}
+
+// ---- scene ----------------------------------------------------------------------------------
+int rtc_scene_clear(rtc_ctx* c)
+{
+    if (!c) return fail(RTC_ERR_INVALID, "ctx is NULL");
+    c->objs.clear();
+    c->scene_dirty = true; c->host_stale = false;
+    return RTC_OK;
+}
+
+int rtc_scene_add_sphere(rtc_ctx* c, const float center[3], float radius, const float rgb[3], float speed, int mover)
+{
+    if (!c || !center || !rgb) return fail(RTC_ERR_INVALID, "NULL argument");
+    int rc = refresh_host_scene(c);
+    if (rc) return rc;
+    rtc_object o;
+    memset(&o, 0, sizeof o);
+    o.type = RTC_OBJ_SPHERE;
+    for (int i = 0; i < 3; ++i) { o.center[i] = center[i]; o.color[i] = rgb[i]; }
+    o.radius = radius; o.speed = speed; o.mover = mover;
+    c->objs.push_back(o);
+    c->scene_dirty = true;
+    return RTC_OK;
+}
+
+int rtc_scene_add_plane(rtc_ctx* c, const float center[3], const float normal[3], const float rgb[3], float width, float height)
+{
+    if (!c || !center || !normal || !rgb) return fail(RTC_ERR_INVALID, "NULL argument");
+    int rc = refresh_host_scene(c);
+    if (rc) return rc;
+    rtc_object o;
+    memset(&o, 0, sizeof o);
+    o.type = RTC_OBJ_PLANE;
+    for (int i = 0; i < 3; ++i) { o.center[i] = center[i]; o.color[i] = rgb[i]; }
+    // Vector3::Normalize with its zero check (Plane.cu:9, MyMath.h:117-123).
+    const float len = sqrtf(normal[0] * normal[0] + normal[1] * normal[1] + normal[2] * normal[2]);
+    const float div = len < 0.000001f ? 0.0f : 1.0f / len;
+    for (int i = 0; i < 3; ++i) o.normal[i] = normal[i] * div;
+    o.width = width; o.height = height;
+    c->objs.push_back(o);
+    c->scene_dirty = true;
+    return RTC_OK;
+}
+
+int rtc_scene_set_objects(rtc_ctx* c, const rtc_object* objs, uint32_t n)
+{
+    if (!c || (n && !objs)) return fail(RTC_ERR_INVALID, "NULL argument");
+    for (uint32_t i = 0; i < n; ++i)
+        if (objs[i].type != RTC_OBJ_SPHERE && objs[i].type != RTC_OBJ_PLANE)
+            return fail(RTC_ERR_INVALID, "object %u has unknown type %d", i, objs[i].type);
+    c->objs.assign(objs, objs + n);
+    c->scene_dirty = true; c->host_stale = false;
+    return RTC_OK;
+}
+
+int rtc_scene_get_objects(rtc_ctx* c, rtc_object* out, uint32_t cap, uint32_t* n)
+{
+    if (!c) return fail(RTC_ERR_INVALID, "ctx is NULL");
+    int rc = refresh_host_scene(c);
+    if (rc) return rc;
+    if (n) *n = (uint32_t)c->objs.size();
+    if (out) memcpy(out, c->objs.data(), sizeof(rtc_object) * (c->objs.size() < cap ? c->objs.size() : cap));
+    return RTC_OK;
+}
+
+int rtc_scene_count(rtc_ctx* c, uint32_t* n)
+{
+    if (!c || !n) return fail(RTC_ERR_INVALID, "NULL argument");
+    *n = (uint32_t)c->objs.size();
+    return RTC_OK;
+}
+
+int rtc_update_objects(rtc_ctx* c, double dt, uint32_t flags)
+{
+    if (!c) return fail(RTC_ERR_INVALID, "ctx is NULL");
+    CK(cudaSetDevice(c->device));
+    const size_t n = c->objs.size();
+    // The reference launches UpdateObjects with block = count threads: invalid for count > 1024
+    // (and for 0), so nothing moves (RayTracingManager.cu:89-107).
+    if ((flags & RTC_FLAG_UPDATE_REF_LAUNCH_LIMIT) && (n > 1024 || n == 0)) return RTC_OK;
+    int rc = upload_scene(c);
+    if (rc) return rc;
+    CK(rtc::launch_update_objects(c->stream, c->d_objs.p, (int)n, dt));
+    c->host_stale = true;
+    return RTC_OK;
+}
+
+// ---- frame ------------------------------------------------------------------------------------
+int rtc_render(rtc_ctx* c, const rtc_params* p, rtc_mode mode, uint32_t flags)
+{
+    if (!c) return fail(RTC_ERR_INVALID, "ctx is NULL");
+    if (!p) return fail(RTC_ERR_INVALID, "params is NULL");
+    CK(cudaSetDevice(c->device));
+    if (p->x < 1 || p->y < 1) return fail(RTC_ERR_INVALID, "invalid console size %ux%u", p->x, p->y);
+    if ((uint64_t)(p->x - 1u) * p->y >= (1ull << 31)) return fail(RTC_ERR_CAPACITY, "console size too large");
+    const uint32_t W = p->x - 1u;
+    const size_t n_px = (size_t)W * p->y;
+    const size_t cap = rtc_encode_capacity(p->x, p->y, mode);
+    CK(c->d_color.ensure(n_px * mode_bpp(mode) + 16));
+    if (mode_has_glyph(mode)) CK(c->d_glyph.ensure(n_px + 16));
+    CK(c->d_out.ensure(cap));
+    CK(c->d_desc.ensure(rtc::encode_state_bytes(n_px) / sizeof(unsigned long long)));
+    c->have_frame = false;
+    int rc = trace_shade(c, p, mode, flags, 0, p->y, c->d_color.p, mode_has_glyph(mode) ? c->d_glyph.p : nullptr, true);
+    if (rc) return rc;
+    CK(rtc::launch_encode(c->stream, c->d_color.p, mode_has_glyph(mode) ? c->d_glyph.p : nullptr, p->x, p->y, mode,
+                          c->d_out.p, cap, c->d_total.p, c->d_desc.p, c->d_counters.p + 32, &c->enc_ticket_base,
+                          &c->enc_epoch));
+    c->last_launches++;
+    CK(cudaEventRecord(c->ev[4], c->stream));
+    CK(cudaMemcpyAsync(c->h_total.p, c->d_total.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    c->have_frame = true;
+    c->timings_valid = true;
+    c->last_mode = mode; c->last_x = p->x; c->last_y = p->y; c->last_cap = cap;
+    return RTC_OK;
+}
+
+int rtc_frame_ansi_device(rtc_ctx* c, const char** dev_ptr, size_t* n_bytes)
+{
+    if (!c || !dev_ptr || !n_bytes) return fail(RTC_ERR_INVALID, "NULL argument");
+    if (!c->have_frame) return fail(RTC_ERR_INVALID, "no frame rendered");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    const size_t n = (size_t)c->h_total.p[0];
+    if (n > c->last_cap) return fail(RTC_ERR_CAPACITY, "stream (%zu B) exceeds capacity (%zu B)", n, c->last_cap);
+    *dev_ptr = c->d_out.p; *n_bytes = n;
+    return RTC_OK;
+}
+
+int rtc_frame_ansi(rtc_ctx* c, const char** host_ptr, size_t* n_bytes)
+{
+    const char* dptr = nullptr;
+    size_t n = 0;
+    int rc = rtc_frame_ansi_device(c, &dptr, &n);
+    if (rc) return rc;
+    CK(c->h_out.ensure(n > 0 ? n : 1));
+    if (n) CK(cudaMemcpyAsync(c->h_out.p, dptr, n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *host_ptr = c->h_out.p; *n_bytes = n;
+    return RTC_OK;
+}
+
+int rtc_frame_color(rtc_ctx* c, const uint8_t** host_color, uint32_t* bpp, const uint8_t** host_glyph)
+{
+    if (!c) return fail(RTC_ERR_INVALID, "ctx is NULL");
+    if (!c->have_frame) return fail(RTC_ERR_INVALID, "no frame rendered");
+    CK(cudaSetDevice(c->device));
+    const size_t n_px = (size_t)(c->last_x - 1u) * c->last_y;
+    const uint32_t b = mode_bpp(c->last_mode);
+    CK(c->h_color.ensure(n_px * b + 1));
+    if (n_px && c->last_mode != RTC_SDL)
+        CK(cudaMemcpyAsync(c->h_color.p, c->d_color.p, n_px * b, cudaMemcpyDeviceToHost, c->stream));
+    const bool gl = mode_has_glyph(c->last_mode);
+    if (gl) {
+        CK(c->h_glyph.ensure(n_px + 1));
+        if (n_px) CK(cudaMemcpyAsync(c->h_glyph.p, c->d_glyph.p, n_px, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    if (host_color) *host_color = c->h_color.p;
+    if (bpp) *bpp = b;
+    if (host_glyph) *host_glyph = gl ? c->h_glyph.p : nullptr;
+    return RTC_OK;
+}
+
+int rtc_frame_hits(rtc_ctx* c, const float** host_dist, const int32_t** host_index)
+{
+    if (!c) return fail(RTC_ERR_INVALID, "ctx is NULL");
+    if (!c->have_frame) return fail(RTC_ERR_INVALID, "no frame rendered");
+    CK(cudaSetDevice(c->device));
+    const size_t n_px = (size_t)(c->last_x - 1u) * c->last_y;
+    CK(c->h_hit_t.ensure(n_px + 1));
+    CK(c->h_hit_idx.ensure(n_px + 1));
+    if (n_px) {
+        CK(cudaMemcpyAsync(c->h_hit_t.p, c->d_hit_t.p, n_px * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(c->h_hit_idx.p, c->d_hit_idx.p, n_px * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    if (host_dist) *host_dist = c->h_hit_t.p;
+    if (host_index) *host_index = c->h_hit_idx.p;
+    return RTC_OK;
+}
+
+int rtc_update(rtc_ctx* c, const rtc_params* p, rtc_mode mode, double dt, uint32_t flags,
+               const char** host_ptr, size_t* n_bytes)
+{
+    // RayTracingManager::Update runs the physics step unconditionally, even for dt == 0 (where it
+    // still clamps every sphere's y into [-10,10], Sphere.cu:18-22) -- so does this.
+    int rc = rtc_update_objects(c, dt, flags);
+    if (rc) return rc;
+    rc = rtc_render(c, p, mode, flags);
+    if (rc) return rc;
+    return rtc_frame_ansi(c, host_ptr, n_bytes);
+}
+
+int rtc_last_timings(rtc_ctx* c, rtc_timings* out)
+{
+    if (!c || !out) return fail(RTC_ERR_INVALID, "NULL argument");
+    if (!c->timings_valid) return fail(RTC_ERR_INVALID, "no frame rendered");
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventSynchronize(c->ev[4]));
+    CK(cudaEventElapsedTime(&out->prep_ms, c->ev[0], c->ev[1]));
+    CK(cudaEventElapsedTime(&out->trace_ms, c->ev[1], c->ev[2]));
+    CK(cudaEventElapsedTime(&out->shade_ms, c->ev[2], c->ev[3]));
+    CK(cudaEventElapsedTime(&out->encode_ms, c->ev[3], c->ev[4]));
+    CK(cudaEventElapsedTime(&out->total_ms, c->ev[0], c->ev[4]));
+    out->launches = c->last_launches;
+    return RTC_OK;
+}
+
+// ---- stage-level entry points -------------------------------------------------------------------
+int rtc_trace_band(rtc_ctx* c, const rtc_params* p, rtc_mode mode, uint32_t flags, uint32_t row0, uint32_t row1,
+                   uint8_t* dev_color, uint8_t* dev_glyph)
+{
+    if (!c) return fail(RTC_ERR_INVALID, "ctx is NULL");
+    if (!dev_color && mode != RTC_SDL) return fail(RTC_ERR_INVALID, "dev_color is NULL");
+    if (mode_has_glyph(mode) && !dev_glyph) return fail(RTC_ERR_INVALID, "dev_glyph is NULL in an ASCII mode");
+    CK(cudaSetDevice(c->device));
+    return trace_shade(c, p, mode, flags, row0, row1, dev_color, dev_glyph, false);
+}
+
+int rtc_encode(rtc_ctx* c, const uint8_t* dev_color, const uint8_t* dev_glyph, uint32_t x, uint32_t y, rtc_mode mode,
+               char* dev_out, size_t cap, unsigned long long* dev_total)
+{
+    if (!c) return fail(RTC_ERR_INVALID, "ctx is NULL");
+    if (!dev_out || !dev_total) return fail(RTC_ERR_INVALID, "NULL output");
+    if (x < 1 || y < 1) return fail(RTC_ERR_INVALID, "invalid console size %ux%u", x, y);
+    if (mode < RTC_BIT_ASCII || mode > RTC_SDL) return fail(RTC_ERR_INVALID, "invalid rendering mode %d", mode);
+    if (mode != RTC_SDL && x > 1 && !dev_color) return fail(RTC_ERR_INVALID, "dev_color is NULL");
+    if ((uint64_t)(x - 1u) * y >= (1ull << 31)) return fail(RTC_ERR_CAPACITY, "console size too large");
+    CK(cudaSetDevice(c->device));
+    CK(c->d_desc.ensure(rtc::encode_state_bytes((uint64_t)(x - 1u) * y) / sizeof(unsigned long long)));
+    CK(rtc::launch_encode(c->stream, dev_color, dev_glyph, x, y, mode, dev_out, cap, dev_total, c->d_desc.p,
+                          c->d_counters.p + 32, &c->enc_ticket_base, &c->enc_epoch));
+    return RTC_OK;
+}
+
+int rtc_ipc_export(rtc_ctx* c, void* dev_ptr, unsigned char handle_out[64])
+{
+    if (!c || !dev_ptr || !handle_out) return fail(RTC_ERR_INVALID, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CK(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, dev_ptr));
+    memcpy(handle_out, &h, 64);
+    return RTC_OK;
+}
+
+int rtc_ipc_open(rtc_ctx* c, const unsigned char handle[64], void** dev_ptr)
+{
+    if (!c || !handle || !dev_ptr) return fail(RTC_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CK(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return RTC_OK;
+}
+
+int rtc_ipc_close(rtc_ctx* c, void* dev_ptr)
+{
+    if (!c || !dev_ptr) return fail(RTC_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaIpcCloseMemHandle(dev_ptr));
+    return RTC_OK;
+}
+
+int rtc_camera_params(uint32_t x, uint32_t y, const float pos[3], const float rot[3], float pixel_aspect, rtc_params* out)
+{
+    const int rc = rtc::camera_params(x, y, pos, rot, pixel_aspect, out);
+    if (rc) return fail(rc, "camera_params: invalid argument or singular view matrix");
+    return RTC_OK;
+}
+
+int rtc_fp32_peak(rtc_ctx* c, int variant, int iters, float* tflops, float* ms)
+{
+    if (!c || !tflops) return fail(RTC_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    const int n_ctas = c->sm_count * 4;
+    CK(rtc::launch_fp32_peak(c->stream, variant, n_ctas, iters > 8 ? 8 : iters, c->d_sink.p));   // warm-up
+    CK(cudaEventRecord(c->ev[5], c->stream));
+    CK(rtc::launch_fp32_peak(c->stream, variant, n_ctas, iters, c->d_sink.p));
+    cudaEvent_t end;
+    CK(cudaEventCreate(&end));
+    CK(cudaEventRecord(end, c->stream));
+    CK(cudaEventSynchronize(end));
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, c->ev[5], end));
+    cudaEventDestroy(end);
+    if (ms) *ms = t;
+    *tflops = (float)(rtc::fp32_peak_flops(variant, n_ctas, iters) / (t * 1e-3) / 1e12);
+    return RTC_OK;
+}
+
+}  // extern "C"

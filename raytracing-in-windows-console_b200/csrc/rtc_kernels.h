@@ -1,0 +1,52 @@
+// rtc_kernels.h -- host-side launchers of the sm_100a kernels (internal to librtc_b200).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rtc.h"
+
+namespace rtc {
+
+struct FrameParams;
+
+constexpr int kMaxSlotsPerLaunch = 8192;   // sphere slots resident in shared memory per trace launch
+constexpr int kNumCounters = 64;           // per-frame device counters zeroed by the hoist kernel
+
+// kernel 0 / 1 (rtc_trace.cu)
+cudaError_t configure_trace();
+size_t trace_smem_bytes(int n_slots);
+cudaError_t launch_hoist(cudaStream_t st, const rtc_object* objs, const int32_t* sphere_obj, int n_spheres,
+                         int n_slots, const float cam[3], float4* sph_pairs, float* sph_c,
+                         unsigned int* counters, int n_counters);
+cudaError_t launch_trace(cudaStream_t st, int n_ctas, const FrameParams& fp, const float4* g_pairs, const float* g_c,
+                         const int32_t* sphere_obj, int n_spheres, int n_slots, const rtc_object* objs,
+                         const int32_t* plane_obj, int n_planes, float* hit_t, int32_t* hit_idx,
+                         unsigned int* tile_counter, int carry_in);
+
+// kernel 2 (rtc_shade.cu)
+cudaError_t launch_shade(cudaStream_t st, const FrameParams& fp, int mode, uint32_t flags,
+                         const rtc_object* objs, int n_objs, const float* hit_t, const int32_t* hit_idx,
+                         uint8_t* color, uint8_t* glyph);
+
+// kernel 3 (rtc_encode.cu)
+cudaError_t configure_encode();
+size_t encode_state_bytes(uint64_t n_cells);
+// `desc`: encode_state_bytes() of device memory (never needs clearing: descriptors are epoch-tagged);
+// `ticket`: one device uint32 that only ever counts up; *ticket_base / *epoch: host-side mirrors.
+cudaError_t launch_encode(cudaStream_t st, const uint8_t* color, const uint8_t* glyph, uint32_t x, uint32_t y,
+                          int mode, char* out, size_t cap, unsigned long long* total, unsigned long long* desc,
+                          unsigned int* ticket, unsigned int* ticket_base, unsigned int* epoch);
+
+// physics (rtc_shade.cu)
+cudaError_t launch_update_objects(cudaStream_t st, rtc_object* objs, int n, double dt);
+
+// microbenchmarks (rtc_microbench.cu)
+cudaError_t launch_fp32_peak(cudaStream_t st, int variant, int n_ctas, int iters, float* sink);
+
+}  // namespace rtc
+
+namespace rtc {
+double fp32_peak_flops(int variant, int n_ctas, int iters);
+// Camera3D math on the host (rtc_camera.cpp)
+int camera_params(uint32_t x, uint32_t y, const float pos[3], const float rot[3], float pixel_aspect, rtc_params* out);
+}  // namespace rtc

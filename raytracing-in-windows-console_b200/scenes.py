@@ -107,49 +107,11 @@ def config_scene(name):
 
 
 def camera_params(x, y, pos, rot, pixel_aspect=0.0):
-    """Camera3D::Init/Update/GetInverseVMatrix + Engine3D::Render's block (reference
-    Camera3D.cpp:8-48,:51-98,:207-376; Engine3D.cpp:88-97), restated in float32 numpy.
-    Mirrors the C++ facade (host/Camera3D.cpp); tests check both against the oracle."""
-    f = np.float32
-    k = f(0.01) if pixel_aspect == 0.0 else f(pixel_aspect)
-    fov = f(math.pi) / f(1.5)
-    width, height = f(x), f(y)
-    aspect = width / (k * width * height)
-    e = f(1.0) / np.tan(fov / f(2.0), dtype=np.float32)
-    p, yw = f(rot[0]), f(rot[1])
-    s, c = (lambda a: np.sin(a, dtype=np.float32)), (lambda a: np.cos(a, dtype=np.float32))
-    fwd = [-s(yw), -s(p) * c(yw), -c(p) * c(yw)]
-    right = [c(yw), -s(p) * s(yw), -c(p) * s(yw)]
-    up = [f(0.0), c(p), -s(p)]
-    m = np.array(
-        [[right[0], up[0], fwd[0], f(pos[0])],
-         [right[1], up[1], fwd[1], f(pos[1])],
-         [right[2], up[2], fwd[2], f(pos[2])],
-         [0, 0, 0, 1]], np.float32)
-    inv = np.zeros((4, 4), np.float32)
-    for r in range(4):
-        for cc in range(4):
-            R = [i for i in range(4) if i != cc]
-            C = [i for i in range(4) if i != r]
-            t1 = m[R[0], C[0]] * m[R[1], C[1]] * m[R[2], C[2]]
-            t2 = m[R[0], C[0]] * m[R[1], C[2]] * m[R[2], C[1]]
-            t3 = m[R[1], C[0]] * m[R[0], C[1]] * m[R[2], C[2]]
-            t4 = m[R[1], C[0]] * m[R[0], C[2]] * m[R[2], C[1]]
-            t5 = m[R[2], C[0]] * m[R[0], C[1]] * m[R[1], C[2]]
-            t6 = m[R[2], C[0]] * m[R[0], C[2]] * m[R[1], C[1]]
-            inv[r, cc] = (-t1 + t2 + t3 - t4 - t5 + t6) if (r + cc) & 1 else (t1 - t2 - t3 + t4 + t5 - t6)
-    det = m[0, 0] * inv[0, 0] + m[0, 1] * inv[1, 0] + m[0, 2] * inv[2, 0] + m[0, 3] * inv[3, 0]
-    inv = (inv * (f(1.0) / det)).astype(np.float32)
-    out = RtcParams()
-    for i, v in enumerate(inv.reshape(-1)):
-        out.inv_view[i] = float(v)
-    for i in range(3):
-        out.cam_pos[i] = float(f(pos[i]))
-    out.x, out.y = x, y
-    out.element1 = float(e / aspect)
-    out.element2 = float(e)
-    out.cam_far = 250.0
-    return out
+    """Camera3D::Init/Update/GetInverseVMatrix + Engine3D::Render's parameter block (reference
+    Camera3D.cpp:8-48,:51-98,:207-376; Engine3D.cpp:88-97) -- computed by the library's host code
+    (csrc/rtc_camera.cpp via rtc_camera_params; no GPU needed)."""
+    from . import camera_params as _camera_params
+    return _camera_params(x, y, pos, rot, pixel_aspect)
 
 
 def config_camera(name, frame=0, n_frames=120):

@@ -1,0 +1,295 @@
+"""GPU (-m gpu): the CUDA path, called through the C-ABI, against the CPU oracle and the golden
+vectors made by the reference itself.
+
+Bars (BASELINE.json north_star):
+  * hit/miss decisions, accepted object index and hit distance: IDENTICAL (bit-exact);
+  * quantised colour: within +-1 LSB per channel (the only non-bit-exact operation is pow(x,32),
+    computed correctly rounded on the GPU vs the host libm in the oracle); in practice identical;
+  * ANSI stream: bit-exact given identical colour planes.
+"""
+import numpy as np
+import pytest
+
+from rtc_b200 import scenes
+from rtc_b200._types import (BIT_ASCII, BIT_PIXEL, FLAG_SHADOWS, FLAG_UPDATE_REF_LAUNCH_LIMIT, MODE_NAMES,
+                             OBJECT_DTYPE, RGB_ASCII, RGB_NORMALS, RGB_PIXEL, SDL, mode_bpp, mode_cell, mode_has_glyph)
+from util import PI32, objs_from_bytes, params_from_bytes, parse_stream
+
+pytestmark = pytest.mark.gpu
+
+RGB_TOL = 1          # LSB per channel, stated tolerance for the floating-point part of the path
+MAX_OFF_FRACTION = 1e-4
+
+
+def check_frame(ctx, oracle, objs, p, mode, flags=0, expect_stream=None):
+    x, y = p.x, p.y
+    n_px = (x - 1) * y
+    ctx.set_objects(objs)
+    ctx.render(p, mode, flags)
+    stream = ctx.frame_ansi()
+    dist, index = ctx.frame_hits(n_px)
+    o = oracle.trace_planes(objs, p, mode, flags)
+    # --- hit records: bit-exact
+    assert np.array_equal(index, o["index"]), f"{MODE_NAMES[mode]}: accepted object differs on {(index != o['index']).sum()} rays"
+    assert dist.tobytes() == o["dist"].tobytes(), f"{MODE_NAMES[mode]}: hit distance differs"
+    if mode == SDL:
+        assert stream.tobytes() == b"\n" * y
+        return stream
+    color, glyph = ctx.frame_color(n_px)
+    # --- colour planes: +-1 LSB on at most a sliver of pixels (expected: identical)
+    if mode in (BIT_ASCII, BIT_PIXEL):
+        n_off = int((color != o["color"]).sum())     # an xterm index may flip when RGB moves by 1 LSB
+    else:
+        diff = np.abs(color.astype(np.int16) - o["color"].astype(np.int16))
+        assert diff.max(initial=0) <= RGB_TOL, f"{MODE_NAMES[mode]}: colour off by {diff.max()} LSB"
+        n_off = int((diff != 0).sum())
+    assert n_off <= max(2, MAX_OFF_FRACTION * n_px), f"{MODE_NAMES[mode]}: {n_off} colour bytes differ from the oracle"
+    if mode_has_glyph(mode):
+        assert np.array_equal(glyph, o["glyph"])
+    # --- stream: bit-exact given the GPU's own planes ...
+    assert np.array_equal(stream, oracle.encode_planes(color, glyph, x, y, mode)), "ANSI stream differs given identical planes"
+    # ... and, when the planes are identical (the expected case), equal to the oracle's full path
+    if n_off == 0:
+        want = oracle.render(objs, p, mode, flags) if expect_stream is None else expect_stream
+        assert np.array_equal(stream, want), "ANSI stream differs from the reference path"
+    return stream
+
+
+@pytest.mark.parametrize("size", [(240, 64), (400, 150)])
+@pytest.mark.parametrize("mode", range(6))
+def test_default_scene_vs_golden(ctx, oracle, golden, size, mode):
+    x, y = size
+    p = params_from_bytes(golden[f"default_{x}x{y}_params"])
+    objs = scenes.default_scene()
+    ctx.set_objects(objs)
+    stream = np.array(ctx.update(p, mode, dt=0.0, flags=FLAG_UPDATE_REF_LAUNCH_LIMIT))   # == RayTracingManager::Update
+    assert np.array_equal(stream, golden[f"default_{x}x{y}_m{mode}_stream"]), \
+        f"{MODE_NAMES[mode]} {x}x{y}: stream differs from the reference's"
+    after = ctx.get_objects()
+    check_frame(ctx, oracle, after, p, mode, expect_stream=golden[f"default_{x}x{y}_m{mode}_stream"])
+
+
+def test_random_scenes_vs_golden(ctx, oracle, golden):
+    for k in range(int(golden["n_cases"][0])):
+        objs = objs_from_bytes(golden[f"case{k}_objs"])
+        p = params_from_bytes(golden[f"case{k}_params"])
+        dt = float(golden[f"case{k}_dt"][0])
+        for mode in range(5):
+            ctx.set_objects(objs)
+            stream = np.array(ctx.update(p, mode, dt=dt, flags=FLAG_UPDATE_REF_LAUNCH_LIMIT))
+            assert ctx.get_objects().tobytes() == golden[f"case{k}_objs_after"].tobytes(), f"case {k}: physics differs"
+            assert np.array_equal(stream, golden[f"case{k}_m{mode}_stream"]), f"case {k} {MODE_NAMES[mode]}"
+            if mode in (0, 2, 4):
+                color, glyph = ctx.frame_color((p.x - 1) * p.y)
+                assert np.array_equal(color, golden[f"case{k}_m{mode}_color"])
+                if mode != 4:
+                    assert np.array_equal(glyph, golden[f"case{k}_m{mode}_glyph"])
+
+
+@pytest.mark.parametrize("name", ["config2_1080p_64"])
+def test_bench_config_small(ctx, oracle, name):
+    """Config 2 (1921x1080, 64 spheres + plane) against the oracle, whole frame."""
+    objs = scenes.config_scene(name)
+    p = scenes.config_camera(name)
+    check_frame(ctx, oracle, objs, p, RGB_PIXEL)
+
+
+def test_many_spheres_band(ctx, oracle):
+    """Config-3 scene (1024 spheres + plane): a band of rows against the oracle (full frame is too slow on CPU)."""
+    objs = scenes.config_scene("config3_4k_1024")
+    p = scenes.config_camera("config3_4k_1024")
+    ctx.set_objects(objs)
+    ctx.render(p, RGB_PIXEL)
+    n_px = (p.x - 1) * p.y
+    dist, index = ctx.frame_hits(n_px)
+    color, _ = ctx.frame_color(n_px)
+    W = p.x - 1
+    for (r0, r1) in [(0, 4), (1078, 1084), (2150, 2160)]:
+        o = oracle.trace_planes(objs, p, RGB_PIXEL, row0=r0, row1=r1)
+        sl = slice(r0 * W, r1 * W)
+        assert np.array_equal(index[sl], o["index"])
+        assert dist[sl].tobytes() == o["dist"].tobytes()
+        d = np.abs(color[r0 * W * 3:r1 * W * 3].astype(np.int16) - o["color"].astype(np.int16))
+        assert d.max() <= RGB_TOL and (d != 0).sum() <= 2
+    # size-independent properties of the full-size stream
+    stream = ctx.frame_ansi()
+    keys, glyphs, full = parse_stream(stream, p.x, p.y, RGB_PIXEL) if False else (None, None, None)   # python decode of 8M cells is too slow
+    assert stream[-1] == 10 and int((stream == 10).sum()) >= p.y
+    assert np.array_equal(stream, oracle.encode_planes(color, None, p.x, p.y, RGB_PIXEL))
+
+
+def test_trace_band_matches_full_frame(ctx, rtc):
+    """Row-band partition (multi-GPU building block): bands written at their offsets == the full frame."""
+    import torch
+    objs = scenes.config_scene("config2_1080p_64")
+    x, y = 481, 270
+    p = rtc.camera_params(x, y, (0, 0, -120), (0, PI32, 0), 1.0 / (x - 1))
+    W = x - 1
+    ctx.set_objects(objs)
+    for mode in (RGB_PIXEL, RGB_ASCII, BIT_ASCII):
+        ctx.render(p, mode)
+        full_color, full_glyph = ctx.frame_color(W * y)
+        want = ctx.frame_ansi()
+        bpp = mode_bpp(mode)
+        color = torch.zeros(W * y * bpp, dtype=torch.uint8, device="cuda")
+        glyph = torch.zeros(W * y, dtype=torch.uint8, device="cuda")
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        for (r0, r1) in [(0, 67), (67, 135), (135, 136), (136, 270)]:      # ragged bands
+            ctx.trace_band(p, mode, r0, r1, color.data_ptr() + r0 * W * bpp, glyph.data_ptr() + r0 * W)
+        cap = rtc.encode_capacity(x, y, mode)
+        out = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+        total = torch.zeros(1, dtype=torch.int64, device="cuda")
+        ctx.encode(color.data_ptr(), glyph.data_ptr() if mode_has_glyph(mode) else 0, x, y, mode, out.data_ptr(), cap, total.data_ptr())
+        torch.cuda.synchronize()
+        ctx.set_stream(0)
+        assert np.array_equal(color.cpu().numpy(), full_color)
+        n = int(total.item())
+        assert np.array_equal(out[:n].cpu().numpy(), want)
+
+
+def test_encoder_edge_cases(ctx, oracle, rtc):
+    """Encoder alone on hand-made planes: ragged sizes, 1-cell rows, long runs, every-cell-differs,
+    tile boundaries (2048-cell tiles), unaligned plane pointers."""
+    import torch
+    rng = np.random.default_rng(11)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    cases = [(2, 1), (2, 9), (3, 3), (18, 5), (2049, 1), (2050, 2), (4097, 3), (700, 37), (1025, 16)]
+    for (x, y) in cases:
+        W = x - 1
+        for mode in (RGB_PIXEL, RGB_ASCII, BIT_PIXEL, BIT_ASCII):
+            bpp = mode_bpp(mode)
+            for pattern in ("noise", "runs", "constant"):
+                if pattern == "noise":
+                    keys = rng.integers(0, 256, W * y * bpp).astype(np.uint8)
+                elif pattern == "runs":
+                    keys = np.repeat(rng.integers(0, 256, (W * y + 36) // 37 * bpp).astype(np.uint8).reshape(-1, bpp), 37, 0)[:W * y].reshape(-1)
+                else:
+                    keys = np.full(W * y * bpp, 200, np.uint8)
+                glyph = rng.choice(np.frombuffer(b"  .:#@", np.uint8), W * y) if mode_has_glyph(mode) else None
+                for off in (0, 5):                                  # 5: deliberately unaligned device pointers
+                    dk = torch.zeros(keys.size + 16, dtype=torch.uint8, device="cuda")
+                    dk[off:off + keys.size] = torch.from_numpy(keys).cuda()
+                    dg = None
+                    if glyph is not None:
+                        dg = torch.zeros(glyph.size + 16, dtype=torch.uint8, device="cuda")
+                        dg[off:off + glyph.size] = torch.from_numpy(glyph).cuda()
+                    cap = rtc.encode_capacity(x, y, mode)
+                    out = torch.zeros(cap + 16, dtype=torch.uint8, device="cuda")
+                    total = torch.zeros(1, dtype=torch.int64, device="cuda")
+                    ctx.encode(dk.data_ptr() + off, (dg.data_ptr() + off) if dg is not None else 0, x, y, mode,
+                               out.data_ptr() + (off % 3), cap, total.data_ptr())
+                    torch.cuda.synchronize()
+                    n = int(total.item())
+                    got = out[(off % 3):(off % 3) + n].cpu().numpy()
+                    want = oracle.encode_planes(keys, glyph, x, y, mode)
+                    assert np.array_equal(got, want), (x, y, MODE_NAMES[mode], pattern, off)
+    ctx.set_stream(0)
+
+
+def test_encoder_full_size_properties(ctx, oracle, rtc):
+    """Config 5 (7681x4320) worst case: i.i.d. random RGB -> almost every cell emits 20 bytes.
+    Size-independent checks: length formula, newline count/positions, random windows decoded."""
+    import torch
+    x, y = 7681, 4320
+    W = x - 1
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    rgb = torch.randint(0, 256, (W * y * 3,), dtype=torch.uint8, device="cuda", generator=g)
+    cap = rtc.encode_capacity(x, y, RGB_PIXEL)
+    out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    total = torch.zeros(1, dtype=torch.int64, device="cuda")
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.encode(rgb.data_ptr(), 0, x, y, RGB_PIXEL, out.data_ptr(), cap, total.data_ptr())
+    torch.cuda.synchronize()
+    ctx.set_stream(0)
+    n = int(total.item())
+    px = rgb.view(-1, 3)
+    full = torch.ones(W * y, dtype=torch.bool, device="cuda")
+    full[1:] = (px[1:] != px[:-1]).any(1)
+    n_full = int(full.sum().item())
+    assert n == 20 * n_full + (W * y - n_full) + y                          # length formula
+    lens = torch.where(full, 20, 1).to(torch.int64)
+    lens.view(y, W)[:, -1] += 1
+    ends = torch.cumsum(lens, 0)
+    row_end = ends.view(y, W)[:, -1] - 1
+    assert bool((out[row_end] == 10).all())                                 # one newline per row, in place
+    # decode random windows and the first/last rows against the oracle on the same cells
+    host = out[:n].cpu().numpy()
+    starts = (ends - lens).cpu().numpy()
+    rgb_h = rgb.cpu().numpy()
+    for row in [0, 1, y // 2, y - 1]:
+        a, b = int(starts[row * W]), int(ends[(row + 1) * W - 1])
+        want = oracle.encode_planes(rgb_h[(row * W - (1 if row else 0)) * 3:(row + 1) * W * 3], None,
+                                    W + (2 if row else 1), 1, RGB_PIXEL)
+        if row:                                                             # drop the predecessor cell used as context
+            want = want[20:]
+        assert np.array_equal(host[a:b], want), f"row {row}"
+
+
+def test_update_objects(ctx, oracle):
+    objs = scenes.random_spheres(300, 21)
+    ctx.set_objects(objs)
+    cur = objs
+    for dt in (0.0, 0.37, 1.9, 7.0):
+        ctx.update_objects(dt)
+        cur = oracle.update_objects(cur, dt)
+        assert ctx.get_objects().tobytes() == cur.tobytes()
+    big = scenes.random_spheres(1500, 22)
+    ctx.set_objects(big)
+    ctx.update_objects(0.5, FLAG_UPDATE_REF_LAUNCH_LIMIT)                   # reference launch bug mirrored
+    assert ctx.get_objects().tobytes() == big.tobytes()
+    ctx.update_objects(0.5)                                                 # fixed behaviour
+    assert ctx.get_objects().tobytes() == oracle.update_objects(big, 0.5).tobytes()
+
+
+def test_scene_api(ctx, oracle, rtc):
+    """rtc_scene_add_* (Scene3D::CreateSphere/CreatePlane) == bulk upload."""
+    objs = scenes.default_scene()
+    ctx.clear()
+    for o in objs:
+        if o["type"] == 2:
+            ctx.add_sphere(o["center"], o["radius"], o["color"], o["speed"], o["mover"])
+        else:
+            ctx.add_plane(o["center"], (0.0, 3.0, 0.0), o["color"], o["width"], o["height"])   # un-normalised normal
+    assert ctx.get_objects().tobytes() == objs.tobytes()
+    p = rtc.camera_params(120, 40, (0, 0, 0), (0, PI32, 0))
+    check_frame(ctx, oracle, objs, p, RGB_ASCII)
+
+
+def test_edge_scenes(ctx, oracle, rtc):
+    p = rtc.camera_params(64, 20, (0, 0, 0), (0, PI32, 0))
+    empty = np.zeros(0, OBJECT_DTYPE)
+    for mode in range(6):
+        check_frame(ctx, oracle, empty, p, mode)                            # empty scene: all misses
+    one = np.array([scenes.make_sphere((0, 0, 30), 0.0, (10, 20, 30))], OBJECT_DTYPE)   # zero radius
+    check_frame(ctx, oracle, one, p, RGB_PIXEL)
+    inside = np.array([scenes.make_sphere((0, 0, 1), 50.0, (200, 20, 30))], OBJECT_DTYPE)   # camera inside: invisible (Sphere.cu:57)
+    s = check_frame(ctx, oracle, inside, p, RGB_PIXEL)
+    assert len(s) == 20 + (63 * 20 - 1) + 20                                # one escape, then characters only
+    dup = np.array([scenes.make_sphere((0, 0, 30), 5.0, (10, 200, 30)), scenes.make_sphere((0, 0, 30), 5.0, (200, 10, 30))],
+                   OBJECT_DTYPE)                                            # exact tie: lowest index wins
+    check_frame(ctx, oracle, dup, p, RGB_PIXEL)
+    planes = np.array([scenes.make_plane((0, -5, 30), (0, 1, 0), (50, 60, 70), 80, 80),
+                       scenes.make_plane((0, -5, 30), (0, 1, 0), (250, 60, 70), 80, 80)], OBJECT_DTYPE)
+    check_frame(ctx, oracle, planes, p, RGB_ASCII)
+    tiny = rtc.camera_params(2, 1, (0, 0, 0), (0, PI32, 0))                 # 1 traced cell
+    check_frame(ctx, oracle, scenes.default_scene(), tiny, RGB_PIXEL)
+    ragged = rtc.camera_params(38, 23, (0, 3, -10), (0.2, PI32, 0))         # not a multiple of the 16x16 warp tile
+    for mode in range(5):
+        check_frame(ctx, oracle, scenes.default_scene(), ragged, mode)
+
+
+def test_shadow_extension(ctx, oracle, rtc):
+    """Opt-in extension (not in the reference): shadow rays, against the oracle's definition."""
+    objs = np.concatenate([scenes.default_scene(),
+                           np.array([scenes.make_plane((0, -3, 30), (0, 1, 0), (100, 100, 100), 200, 200)], OBJECT_DTYPE)])
+    p = rtc.camera_params(160, 60, (0, 5, -10), (0.1, PI32, 0))
+    s_on = check_frame(ctx, oracle, objs, p, RGB_PIXEL, flags=FLAG_SHADOWS)
+    s_off = check_frame(ctx, oracle, objs, p, RGB_PIXEL)
+    assert not np.array_equal(s_on, s_off)
+
+
+def test_many_spheres_chunked(ctx, oracle, rtc):
+    """More spheres than one shared-memory chunk (8192): multi-launch carry of the running best."""
+    objs = scenes.random_spheres(9000, 31)
+    p = rtc.camera_params(49, 20, (0, 0, -120), (0, PI32, 0), 1.0 / 48)
+    check_frame(ctx, oracle, objs, p, RGB_PIXEL)
