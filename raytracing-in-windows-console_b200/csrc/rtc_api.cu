@@ -96,8 +96,8 @@ struct rtc_ctx {
     bool host_stale = false;       // device physics ran; host copy must be refreshed before use
     DevBuf<rtc_object> d_objs;
     DevBuf<int32_t> d_sphere_obj, d_plane_obj;
-    DevBuf<float4> d_pairs;
-    DevBuf<float> d_c;
+    DevBuf<float> d_fast;      // 12 B per sphere slot (slots padded to a multiple of 4)
+    DevBuf<float4> d_exact;
 
     // frame buffers
     DevBuf<float> d_hit_t;
@@ -137,12 +137,12 @@ int upload_scene(rtc_ctx* c)
         if (c->objs[i].type == RTC_OBJ_SPHERE) c->sphere_obj.push_back((int32_t)i);
         else if (c->objs[i].type == RTC_OBJ_PLANE) c->plane_obj.push_back((int32_t)i);
     }
-    const size_t n_slots = (c->sphere_obj.size() + 1) & ~(size_t)1;
+    const size_t n_slots = (c->sphere_obj.size() + 3) & ~(size_t)3;
     CK(c->d_objs.ensure(n > 0 ? n : 1));
-    CK(c->d_sphere_obj.ensure(n_slots > 0 ? n_slots : 2));
+    CK(c->d_sphere_obj.ensure(n_slots > 0 ? n_slots : 4));
     CK(c->d_plane_obj.ensure(c->plane_obj.size() > 0 ? c->plane_obj.size() : 1));
-    CK(c->d_pairs.ensure(n_slots > 0 ? n_slots : 2));
-    CK(c->d_c.ensure(n_slots > 0 ? n_slots : 2));
+    CK(c->d_fast.ensure(n_slots > 0 ? 3 * n_slots : 12));
+    CK(c->d_exact.ensure(n_slots > 0 ? n_slots : 4));
     // Pageable sources: cudaMemcpyAsync stages them before returning, so the vectors may change afterwards.
     if (n) CK(cudaMemcpyAsync(c->d_objs.p, c->objs.data(), n * sizeof(rtc_object), cudaMemcpyHostToDevice, c->stream));
     if (!c->sphere_obj.empty())
@@ -190,12 +190,12 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
     const uint32_t W = p->x - 1u;
     const size_t n_px = (size_t)(row1 - row0) * W;
     const int n_spheres = (int)c->sphere_obj.size();
-    const int n_slots = (n_spheres + 1) & ~1;
+    const int n_slots = (n_spheres + 3) & ~3;
     const int n_planes = (int)c->plane_obj.size();
     c->last_launches = 0;
     if (record_events) CK(cudaEventRecord(c->ev[0], c->stream));
-    CK(rtc::launch_hoist(c->stream, c->d_objs.p, c->d_sphere_obj.p, n_spheres, n_slots, p->cam_pos, c->d_pairs.p,
-                         c->d_c.p, c->d_counters.p, 32));
+    CK(rtc::launch_hoist(c->stream, c->d_objs.p, c->d_sphere_obj.p, n_spheres, n_slots, p->cam_pos, c->d_fast.p,
+                         c->d_exact.p, c->d_counters.p, 32));
     c->last_launches++;
     if (record_events) CK(cudaEventRecord(c->ev[1], c->stream));
     if (n_px > 0) {
@@ -209,7 +209,7 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
             const int slots = n_slots - s0 < rtc::kMaxSlotsPerLaunch ? n_slots - s0 : rtc::kMaxSlotsPerLaunch;
             const int sph = n_spheres - s0 < slots ? n_spheres - s0 : slots;
             const bool last = ch == n_chunks - 1;
-            CK(rtc::launch_trace(c->stream, c->sm_count, fp, c->d_pairs.p + s0, c->d_c.p + s0, c->d_sphere_obj.p + s0,
+            CK(rtc::launch_trace(c->stream, c->sm_count, fp, c->d_fast.p + 3 * (size_t)s0, c->d_exact.p + s0, c->d_sphere_obj.p + s0,
                                  sph, slots, c->d_objs.p, c->d_plane_obj.p, last ? n_planes : 0, c->d_hit_t.p,
                                  c->d_hit_idx.p, c->d_counters.p + ch, ch > 0 ? 1 : 0));
             c->last_launches++;
@@ -292,7 +292,7 @@ void rtc_destroy(rtc_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
-    c->d_objs.release(); c->d_sphere_obj.release(); c->d_plane_obj.release(); c->d_pairs.release(); c->d_c.release();
+    c->d_objs.release(); c->d_sphere_obj.release(); c->d_plane_obj.release(); c->d_fast.release(); c->d_exact.release();
     c->d_hit_t.release(); c->d_hit_idx.release(); c->d_color.release(); c->d_glyph.release(); c->d_out.release();
     c->d_desc.release(); c->d_counters.release(); c->d_total.release(); c->d_sink.release();
     c->h_total.release(); c->h_out.release(); c->h_color.release(); c->h_glyph.release();

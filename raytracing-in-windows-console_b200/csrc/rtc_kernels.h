@@ -9,16 +9,16 @@ namespace rtc {
 
 struct FrameParams;
 
-constexpr int kMaxSlotsPerLaunch = 8192;   // sphere slots resident in shared memory per trace launch
+constexpr int kMaxSlotsPerLaunch = 4096;   // sphere slots resident in shared memory per trace launch
 constexpr int kNumCounters = 64;           // per-frame device counters zeroed by the hoist kernel
 
 // kernel 0 / 1 (rtc_trace.cu)
 cudaError_t configure_trace();
 size_t trace_smem_bytes(int n_slots);
 cudaError_t launch_hoist(cudaStream_t st, const rtc_object* objs, const int32_t* sphere_obj, int n_spheres,
-                         int n_slots, const float cam[3], float4* sph_pairs, float* sph_c,
+                         int n_slots, const float cam[3], float* sph_fast, float4* sph_exact,
                          unsigned int* counters, int n_counters);
-cudaError_t launch_trace(cudaStream_t st, int n_ctas, const FrameParams& fp, const float4* g_pairs, const float* g_c,
+cudaError_t launch_trace(cudaStream_t st, int n_ctas, const FrameParams& fp, const float* g_fast, const float4* g_exact,
                          const int32_t* sphere_obj, int n_spheres, int n_slots, const rtc_object* objs,
                          const int32_t* plane_obj, int n_planes, float* hit_t, int32_t* hit_idx,
                          unsigned int* tile_counter, int carry_in);

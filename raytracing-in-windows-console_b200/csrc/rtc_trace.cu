@@ -3,18 +3,24 @@
 // Replaces the hot loop of the reference's RayTrace (RayTracing.cu:81-136) and the
 // Sphere::Trace / Plane::Trace it calls per object (Sphere.cu:30-68, Plane.cu:38-73).
 //
-// Design (B200 / sm_100a):
+// Design (B200 / sm_100a), driven by on-box microbenchmarks (profiles/r01_microbench.md):
 //   * All primary rays share the origin (RayTracing.cu:195), so oc = origin - centre and
 //     c = |oc|^2 - r^2 are per-sphere, per-frame constants: kernel 0 hoists them (bit-identical
 //     to what the reference recomputes per ray).
 //   * Kernel 1 is persistent: one 512-thread CTA per SM keeps the whole sphere list in shared
-//     memory (32 B per sphere PAIR) and walks 16x16-pixel screen tiles, one tile per warp,
-//     8 rays per thread.  The inner loop tests TWO spheres against one ray per packed
-//     instruction (FMUL2 + 3x FFMA2 = 7 FLOP per test, the algorithmic minimum) and folds the
-//     two discriminants into a running maximum with one FMNMX3; one LDS.128 pair (warp
-//     broadcast) feeds 16 tests.  The packed test is only a CONSERVATIVE filter (each sphere's
-//     c is deflated by a rounding-error bound); survivors are re-evaluated with the reference's
-//     exact operation order, so hit decisions and distances are bit-identical to the reference.
+//     memory and walks 16x16-pixel screen tiles, one tile per warp, 8 rays per thread.
+//   * The inner loop tests TWO spheres against one ray per packed instruction (FMUL2/FFMA2).
+//     Measured on B200: an FFMA2 only sustains 1 per 2 cycles when at most one operand pair is
+//     fresh (register-bank limit), and every ALU-pipe instruction (FMNMX3, FSETP, ...) costs
+//     ~2.8 FMA-pipe cycles.  So (a) the loop is operand-major -- 8 consecutive packed ops share
+//     one shared-memory operand (register reuse cache), and (b) hit detection uses NO per-test
+//     ALU work: the sphere vector is pre-scaled by 2^64/sqrt(c') and the ray by 2^64, so
+//     u = d.oc overflows to +-inf exactly when |d.oc| >= sqrt(c') (the discriminant is >= 0);
+//     a NaN-sticky accumulator A = fma(u, 0, A) collects the 16 tests of an iteration on the FMA
+//     pipe and is examined once (one FSETP) per iteration.
+//   * The packed test is only a CONSERVATIVE filter (c' is c deflated by a rounding-error
+//     bound); survivors are re-evaluated with the reference's exact operation order, so hit
+//     decisions and distances are bit-identical to the reference.
 //   * The running best (distance, object index) per ray lives in shared memory: it is touched
 //     only on the (rare) exact path and would otherwise cost 16 registers in the hot loop.
 #include "rtc_device.cuh"
@@ -22,24 +28,29 @@
 
 namespace rtc {
 
-// Relative deflation of c for the conservative filter.  The packed discriminant
-// s'^2 - c (s' fused) differs from the reference's fl(fl(s^2) - fl(a*c)) (s un-fused, a = d.d)
-// by at most ~22 * 2^-24 * |oc|^2 (DESIGN.md "filter bound"); 6e-6 leaves > 4x headroom.
+// Relative deflation of c for the conservative filter.  A reference hit needs
+// fl(fl(s^2)) >= fl(a*c) with s the un-fused dot product and a = d.d; against the fused,
+// scaled u this is implied by |u| >= 2^128 once c is deflated by >= 30.4 * 2^-24 * |oc|^2
+// (DESIGN.md "filter bound"); 6e-6 leaves > 3x headroom.
 #define RTC_FILTER_EPS 6.0e-6f
+#define RTC_TWO64 18446744073709551616.0f
 
 // ---- kernel 0: hoist --------------------------------------------------------------------
-// One thread per sphere slot.  sph_pairs: per pair p two float4: (ocx0,ocx1,ocy0,ocy1),
-// (ocz0,ocz1,nc0,nc1) with nc = -(c - eps*|oc|^2).  sph_c: exact c per sphere.  Slots past
-// n_spheres are never-hit sentinels (nc = -1).
+// One thread per sphere slot (slots are padded to a multiple of 4).
+//   sph_fast : per GROUP of 4 spheres 12 floats: gx[4], gy[4], gz[4] with g = oc * 2^64/sqrt(c')
+//              (three LDS.128 feed two packed sphere pairs)
+//   sph_exact: per sphere float4 (ocx, ocy, ocz, c), exact.
+// Slots past n_spheres are never-hit sentinels (g = 0).  c' <= 0 (camera inside / on the
+// sphere) or non-finite geometry => g = inf: always a candidate, the exact path decides.
 __global__ void __launch_bounds__(256)
 hoist_kernel(const rtc_object* __restrict__ objs, const int32_t* __restrict__ sphere_obj, int n_spheres,
-             int n_slots, float camx, float camy, float camz, float4* __restrict__ sph_pairs,
-             float* __restrict__ sph_c, unsigned int* __restrict__ counters, int n_counters)
+             int n_slots, float camx, float camy, float camz, float* __restrict__ sph_fast,
+             float4* __restrict__ sph_exact, unsigned int* __restrict__ counters, int n_counters)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < n_counters) counters[j] = 0u;     // tile tickets / scan state heads for this frame
+    if (j < n_counters) counters[j] = 0u;     // tile tickets for this frame
     if (j >= n_slots) return;
-    float ocx = 0.f, ocy = 0.f, ocz = 0.f, c = 1.f, nc = -1.f;
+    float ocx = 0.f, ocy = 0.f, ocz = 0.f, c = 1.f, gx = 0.f, gy = 0.f, gz = 0.f;
     if (j < n_spheres) {
         const rtc_object& s = objs[sphere_obj[j]];
         ocx = sub(camx, s.center[0]);                                   // Sphere.cu:34
@@ -47,73 +58,112 @@ hoist_kernel(const rtc_object* __restrict__ objs, const int32_t* __restrict__ sp
         ocz = sub(camz, s.center[2]);
         const float oc2 = vdot(v3(ocx, ocy, ocz), v3(ocx, ocy, ocz));
         c = sub(oc2, mul(s.radius, s.radius));                          // Sphere.cu:37
-        nc = fmaf(RTC_FILTER_EPS, oc2, -c);
-        // NaN/inf geometry: force "always a candidate" so the exact path decides.
-        if (!(nc == nc) || fabsf(nc) > 3.0e38f) nc = 3.0e38f;
+        const float cd = fmaf(-RTC_FILTER_EPS, oc2, c);                 // deflated c'
+        const float inf = __int_as_float(0x7f800000);
+        if (cd > 0.0f && cd < 3.0e38f) {
+            const float g = RTC_TWO64 / sqrtf(cd);
+            gx = ocx * g; gy = ocy * g; gz = ocz * g;
+        } else {
+            gx = gy = gz = inf;
+        }
     }
-    float* base = reinterpret_cast<float*>(sph_pairs + 2 * (j >> 1));
-    const int h = j & 1;
-    base[0 + h] = ocx; base[2 + h] = ocy; base[4 + h] = ocz; base[6 + h] = nc;
-    sph_c[j] = c;
+    float* base = sph_fast + 12 * (j >> 2);
+    const int k = j & 3;
+    base[k] = gx; base[4 + k] = gy; base[8 + k] = gz;
+    sph_exact[j] = make_float4(ocx, ocy, ocz, c);
 }
 
 // ---- kernel 1: trace --------------------------------------------------------------------
 constexpr int kRays = 8;            // rays per thread
 constexpr int kThreads = 512;       // 16 warps, one CTA per SM
 constexpr int kTile = 16;           // warp tile = 16 x 16 pixels
+constexpr int kStateFloats = 6 * kRays * kThreads;   // best_t, best_idx, div2A, dir x/y/z
 
-// Shared-memory layout (dynamic): [pairs float4 x 2*n_pairs][c float x n_slots][state]
-// state: best_t, best_idx, fourA, divTwoA -- each [kRays][kThreads].
+// Shared-memory layout (dynamic): [exact float4 x n_slots][fast 12 B x n_slots][state]
+// state, each [kRays][kThreads]: best_t, best_idx, divTwoA, and the exact ray direction
+// (x, y, z) -- the rare exact path indexes rays dynamically, which registers cannot do.
 struct Smem {
-    float4* pairs;
-    float* c;
+    float4* exact;
+    float4* fast;      // 3 float4 per group of 4 spheres
     float* best_t;
     int* best_idx;
-    float* fourA;
     float* div2A;
+    float* dirx;
+    float* diry;
+    float* dirz;
 };
 __device__ __forceinline__ Smem carve(unsigned char* raw, int n_slots)
 {
     Smem s;
-    s.pairs = reinterpret_cast<float4*>(raw);
-    s.c = reinterpret_cast<float*>(raw + (size_t)n_slots * 16);
-    float* st = s.c + n_slots;
+    s.exact = reinterpret_cast<float4*>(raw);
+    s.fast = s.exact + n_slots;
+    float* st = reinterpret_cast<float*>(s.fast + (n_slots >> 2) * 3);
+    constexpr int n = kRays * kThreads;
     s.best_t = st;
-    s.best_idx = reinterpret_cast<int*>(st + kRays * kThreads);
-    s.fourA = st + 2 * kRays * kThreads;
-    s.div2A = st + 3 * kRays * kThreads;
+    s.best_idx = reinterpret_cast<int*>(st + n);
+    s.div2A = st + 2 * n;
+    s.dirx = st + 3 * n;
+    s.diry = st + 4 * n;
+    s.dirz = st + 5 * n;
     return s;
 }
 
-// Exact re-evaluation of the two spheres of pair `p` for one ray (rare path).
+__device__ __forceinline__ float sqrt_approx(float x)   // MUFU.SQRT, rel. error < 2^-22
+{
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ bool not_finite(float x) { return !(fabsf(x) <= 3.402823466e+38f); }
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+// The rare path: exact re-evaluation of the candidates of one loop iteration (4 spheres x 8 rays).
+// `mask` bit (q*16 + r*2 + h) <=> ray r may hit sphere 4g + 2q + h.
 // Accept rule == reference RayTracing.cu:123 (strict '<', lowest index wins ties), written
 // order-independently as the lexicographic minimum of (distance, object index).
-__device__ __noinline__ void exact_pair(const int32_t* __restrict__ sphere_obj, int n_spheres, int n_slots,
-                                        int p, int slot, float dx, float dy, float dz, float qlo, float qhi)
+// A cheap, rigorous lower bound of the hit distance skips candidates that cannot beat the
+// running best (most of them: a ray pierces ~N/100 spheres but only the nearest matters).
+__device__ __noinline__ void exact_group(const int32_t* __restrict__ sphere_obj, int n_slots, int g, uint32_t mask, int tid)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem s = carve(smem_raw, n_slots);
-    const float4 A = s.pairs[2 * p], B = s.pairs[2 * p + 1];
-    const float fourA = s.fourA[slot], div2A = s.div2A[slot];
-    float best = s.best_t[slot];
-    int bidx = s.best_idx[slot];
-    bool changed = false;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const float q = h ? qhi : qlo;
-        const int j = 2 * p + h;
-        if (!(q >= 0.0f) || j >= n_spheres) continue;
-        const float ocx = h ? A.y : A.x, ocy = h ? A.w : A.z, ocz = h ? B.y : B.x;
+    while (mask) {
+        const int b = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int r = (b >> 1) & 7;
+        const int j = 4 * g + 2 * (b >> 4) + (b & 1);
+        const int slot = r * kThreads + tid;
+        const float4 e = s.exact[j];
+        const float dx = s.dirx[slot], dy = s.diry[slot], dz = s.dirz[slot];
+        const float best = s.best_t[slot];
+        {
+            // t_ref ~ (-s - sqrt(D))/a with a = 1 +- 8u, |s1 - s| <= 6u|oc|, and
+            // D_ref <= s1^2 - c + 23u(|oc|^2 + |c|), so t_lb <= t_ref (DESIGN.md "reject bound").
+            const float s1 = fmaf(dz, e.z, fmaf(dy, e.y, dx * e.x));
+            const float oc2 = fmaf(e.z, e.z, fmaf(e.y, e.y, e.x * e.x));
+            const float q1 = fmaxf(fmaf(s1, s1, fmaf(3.0e-6f, oc2 + fabsf(e.w), -e.w)), 0.0f);
+            const float t_lb = (-s1 - sqrt_approx(q1) * 1.000001f) - 2.0e-6f * (fabsf(s1) + sqrt_approx(oc2) * 1.000001f);
+            if (t_lb * (t_lb >= 0.0f ? 0.999999f : 1.000001f) > best) continue;
+        }
+        const V3 d = v3(dx, dy, dz);
+        const float fourA = mul(4.0f, vdot(d, d));                       // RayTracing.cu:91-92
         float t;
-        if (!sphere_trace_hoisted(ocx, ocy, ocz, s.c[j], v3(dx, dy, dz), fourA, div2A, t)) continue;
-        const int oi = sphere_obj[j];
-        if (t < best || (t == best && oi < bidx)) { best = t; bidx = oi; changed = true; }
+        if (!sphere_trace_hoisted(e.x, e.y, e.z, e.w, d, fourA, s.div2A[slot], t)) continue;
+        if (t < best) { s.best_t[slot] = t; s.best_idx[slot] = sphere_obj[j]; continue; }
+        if (t == best) {
+            const int oi = sphere_obj[j];
+            if (oi < s.best_idx[slot]) s.best_idx[slot] = oi;
+        }
     }
-    if (changed) { s.best_t[slot] = best; s.best_idx[slot] = bidx; }
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-trace_kernel(const FrameParams fp, const float4* __restrict__ g_pairs, const float* __restrict__ g_c,
+trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float4* __restrict__ g_exact,
              const int32_t* __restrict__ sphere_obj, int n_spheres, int n_slots,
              const rtc_object* __restrict__ objs, const int32_t* __restrict__ plane_obj, int n_planes,
              float* __restrict__ hit_t, int32_t* __restrict__ hit_idx, unsigned int* __restrict__ tile_counter,
@@ -124,19 +174,19 @@ trace_kernel(const FrameParams fp, const float4* __restrict__ g_pairs, const flo
     const int tid = threadIdx.x, lane = tid & 31;
 
     // Stage the hoisted sphere list once per CTA (persistent kernel).
-    for (int i = tid; i < n_slots; i += kThreads) {   // n_slots floats4 == 2 * n_pairs
-        s.pairs[i] = g_pairs[i];
-        s.c[i] = g_c[i];
-    }
+    for (int i = tid; i < n_slots; i += kThreads) s.exact[i] = g_exact[i];
+    for (int i = tid; i < (n_slots >> 2) * 3; i += kThreads) s.fast[i] = reinterpret_cast<const float4*>(g_fast)[i];
     __syncthreads();
 
     const uint32_t W = fp.x - 1u;
     const uint32_t rows = fp.row1 - fp.row0;
     const uint32_t tiles_x = (W + kTile - 1) / kTile, tiles_y = (rows + kTile - 1) / kTile;
     const uint32_t n_tiles = tiles_x * tiles_y;
-    const int n_pairs = n_slots >> 1;
+    const int n_groups = n_slots >> 2;
     const V3 o = v3(fp.cam[0], fp.cam[1], fp.cam[2]);
     const uint32_t lx = lane & 15u, ly = lane >> 4;
+    const f32x2 ZERO2 = pack2(0.0f, 0.0f);
+    const uint32_t fast_base = (uint32_t)__cvta_generic_to_shared(s.fast);
 
     for (;;) {
         uint32_t tile = 0;
@@ -147,17 +197,16 @@ trace_kernel(const FrameParams fp, const float4* __restrict__ g_pairs, const flo
         const uint32_t col = tx * kTile + lx;
         const uint32_t colc = col < W ? col : W - 1u;     // clamp: out-of-frame lanes trace a duplicate ray
 
-        float dx[kRays], dy[kRays], dz[kRays];
+        float ex[kRays], ey[kRays], ez[kRays];            // ray direction scaled by 2^64 (exact)
 #pragma unroll
         for (int r = 0; r < kRays; ++r) {
             uint32_t row = fp.row0 + ty * kTile + ly + 2u * r;
             if (row >= fp.row1) row = fp.row1 - 1u;
             const V3 d = initial_direction(fp, row, colc);
-            dx[r] = d.x; dy[r] = d.y; dz[r] = d.z;
-            const float a = vdot(d, d);                                   // RayTracing.cu:91
+            ex[r] = d.x * RTC_TWO64; ey[r] = d.y * RTC_TWO64; ez[r] = d.z * RTC_TWO64;
             const int slot = r * kThreads + tid;
-            s.fourA[slot] = mul(4.0f, a);                                 // :92
-            s.div2A[slot] = dvd(1.0f, mul(2.0f, a));                      // :93
+            s.dirx[slot] = d.x; s.diry[slot] = d.y; s.dirz[slot] = d.z;
+            s.div2A[slot] = dvd(1.0f, mul(2.0f, vdot(d, d)));             // RayTracing.cu:91,93
             float bt = 99999999.f;                                        // RayTracing.h:21
             int bi = -1;
             if (carry_in) {
@@ -168,34 +217,47 @@ trace_kernel(const FrameParams fp, const float4* __restrict__ g_pairs, const flo
             s.best_idx[slot] = bi;
         }
 
-        // ---- hot loop: 2 spheres x 8 rays per iteration -----------------------------------
+        // ---- hot loop: 4 spheres (2 packed pairs) x 8 rays per iteration, operand-major ----------
+        // 64 packed ops (128 issue cycles) + 3 LDS.128 + one NaN check per iteration; measured
+        // 4.37 cycles/test against the 4.0 of a pure FFMA2 stream (profiles/r01_microbench.md).
+        uint32_t fa = fast_base;
 #pragma unroll 2
-        for (int p = 0; p < n_pairs; ++p) {
-            const float4 A = s.pairs[2 * p], B = s.pairs[2 * p + 1];     // LDS.128 x2, warp broadcast
-            const f32x2 OX = pack2(A.x, A.y), OY = pack2(A.z, A.w), OZ = pack2(B.x, B.y), NC = pack2(B.z, B.w);
-            f32x2 q[kRays];
-            float m = -1.0f;
+        for (int g = 0; g < n_groups; ++g, fa += 48u) {
+            const float4 FX = lds128(fa), FY = lds128(fa + 16u), FZ = lds128(fa + 32u);   // warp-broadcast
+            f32x2 u[2][kRays];
+            f32x2 acc0 = ZERO2, acc1 = ZERO2;                           // NaN-sticky "something overflowed"
 #pragma unroll
-            for (int r = 0; r < kRays; ++r) {
-                f32x2 t = mul2(pack2(dx[r], dx[r]), OX);                 // FMUL2  (scalar-broadcast operand)
-                t = fma2(pack2(dy[r], dy[r]), OY, t);                    // FFMA2
-                t = fma2(pack2(dz[r], dz[r]), OZ, t);                    // FFMA2  s' = d . oc   (two spheres)
-                q[r] = fma2(t, t, NC);                                   // FFMA2  s'^2 - c'
-            }
+            for (int q = 0; q < 2; ++q) {
+                const f32x2 GX = q ? pack2(FX.z, FX.w) : pack2(FX.x, FX.y);
+                const f32x2 GY = q ? pack2(FY.z, FY.w) : pack2(FY.x, FY.y);
+                const f32x2 GZ = q ? pack2(FZ.z, FZ.w) : pack2(FZ.x, FZ.y);
 #pragma unroll
-            for (int r = 0; r < kRays; ++r) {
-                float lo, hi;
-                unpack2(q[r], lo, hi);
-                m = max3(m, lo, hi);                                     // FMNMX3
-            }
-            if (m >= 0.0f) {                                             // some ray of this lane may hit
+                for (int r = 0; r < kRays; ++r) u[q][r] = mul2(pack2(ex[r], ex[r]), GX);             // FMUL2 x8, GX reused
 #pragma unroll
-                for (int r = 0; r < kRays; ++r) {
-                    float lo, hi;
-                    unpack2(q[r], lo, hi);
-                    if (fmaxf(lo, hi) >= 0.0f)
-                        exact_pair(sphere_obj, n_spheres, n_slots, p, r * kThreads + tid, dx[r], dy[r], dz[r], lo, hi);
+                for (int r = 0; r < kRays; ++r) u[q][r] = fma2(pack2(ey[r], ey[r]), GY, u[q][r]);    // FFMA2 x8, GY reused
+#pragma unroll
+                for (int r = 0; r < kRays; ++r) u[q][r] = fma2(pack2(ez[r], ez[r]), GZ, u[q][r]);    // FFMA2 x8: +-inf <=> candidate
+#pragma unroll
+                for (int r = 0; r < kRays; ++r) {                                                     // FFMA2 x8: inf*0 -> NaN, sticky
+                    if (r & 1) acc1 = fma2(u[q][r], ZERO2, acc1);
+                    else acc0 = fma2(u[q][r], ZERO2, acc0);
                 }
+            }
+            float alo, ahi;
+            unpack2(add2(acc0, acc1), alo, ahi);
+            if (__any_sync(0xffffffffu, !(alo == ahi))) {                // NaN in either half (both are 0 otherwise)
+                uint32_t mask = 0;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+#pragma unroll
+                    for (int r = 0; r < kRays; ++r) {
+                        float lo, hi;
+                        unpack2(u[q][r], lo, hi);
+                        mask |= not_finite(lo) ? (1u << (q * 16 + r * 2)) : 0u;
+                        mask |= not_finite(hi) ? (1u << (q * 16 + r * 2 + 1)) : 0u;
+                    }
+                }
+                if (mask) exact_group(sphere_obj, n_slots, g, mask, tid);
             }
         }
 
@@ -206,8 +268,9 @@ trace_kernel(const FrameParams fp, const float4* __restrict__ g_pairs, const flo
 #pragma unroll
             for (int r = 0; r < kRays; ++r) {
                 float t;
-                if (plane_trace(pl, o, v3(dx[r], dy[r], dz[r]), t)) {
-                    const int slot = r * kThreads + tid;
+                const int slot = r * kThreads + tid;
+                const V3 d = v3(s.dirx[slot], s.diry[slot], s.dirz[slot]);
+                if (plane_trace(pl, o, d, t)) {
                     const float best = s.best_t[slot];
                     if (t < best || (t == best && oi < s.best_idx[slot])) { s.best_t[slot] = t; s.best_idx[slot] = oi; }
                 }
@@ -235,25 +298,25 @@ cudaError_t configure_trace()   // per device, once per context
 
 size_t trace_smem_bytes(int n_slots)
 {
-    return (size_t)n_slots * 16 + (size_t)n_slots * 4 + (size_t)4 * kRays * kThreads * 4;
+    return (size_t)n_slots * 28 + (size_t)kStateFloats * 4;
 }
 
 cudaError_t launch_hoist(cudaStream_t st, const rtc_object* objs, const int32_t* sphere_obj, int n_spheres,
-                         int n_slots, const float cam[3], float4* sph_pairs, float* sph_c,
+                         int n_slots, const float cam[3], float* sph_fast, float4* sph_exact,
                          unsigned int* counters, int n_counters)
 {
     const int n = n_slots > n_counters ? n_slots : n_counters;
     hoist_kernel<<<(n + 255) / 256, 256, 0, st>>>(objs, sphere_obj, n_spheres, n_slots, cam[0], cam[1], cam[2],
-                                                  sph_pairs, sph_c, counters, n_counters);
+                                                  sph_fast, sph_exact, counters, n_counters);
     return cudaGetLastError();
 }
 
-cudaError_t launch_trace(cudaStream_t st, int n_ctas, const FrameParams& fp, const float4* g_pairs, const float* g_c,
+cudaError_t launch_trace(cudaStream_t st, int n_ctas, const FrameParams& fp, const float* g_fast, const float4* g_exact,
                          const int32_t* sphere_obj, int n_spheres, int n_slots, const rtc_object* objs,
                          const int32_t* plane_obj, int n_planes, float* hit_t, int32_t* hit_idx,
                          unsigned int* tile_counter, int carry_in)
 {
-    trace_kernel<<<n_ctas, kThreads, trace_smem_bytes(n_slots), st>>>(fp, g_pairs, g_c, sphere_obj, n_spheres, n_slots,
+    trace_kernel<<<n_ctas, kThreads, trace_smem_bytes(n_slots), st>>>(fp, g_fast, g_exact, sphere_obj, n_spheres, n_slots,
                                                                       objs, plane_obj, n_planes, hit_t, hit_idx,
                                                                       tile_counter, carry_in);
     return cudaGetLastError();

@@ -1,0 +1,16 @@
+"""Small driver for ncu: a few frames of one config (default config 3)."""
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import rtc_b200
+from rtc_b200 import scenes
+
+name = sys.argv[1] if len(sys.argv) > 1 else "config3_4k_1024"
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+ctx = rtc_b200.Context(0)
+ctx.set_objects(scenes.config_scene(name))
+p = scenes.config_camera(name)
+for _ in range(n):
+    ctx.render(p, rtc_b200.RGB_PIXEL)
+    ctx.frame_ansi_device()
+print(ctx.timings())
