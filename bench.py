@@ -32,8 +32,8 @@ import numpy as np  # noqa: E402
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config3_4k_1024")
     ap.add_argument("--mode", default="RGB_PIXEL")
@@ -199,7 +199,8 @@ def run_ours(args):
     frame_rays = W * y
 
     ctx = rtc_b200.Context(local_rank)            # raises without a GPU: no CPU fallback
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()                  # one explicit stream for torch, NCCL and the rtc kernels
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     ctx.set_objects(objs)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")      # > 126 MB L2

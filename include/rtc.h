@@ -123,8 +123,9 @@ RTC_API int rtc_create(rtc_ctx** out, int device);
 RTC_API void rtc_destroy(rtc_ctx* ctx);
 RTC_API const char* rtc_last_error(void);
 RTC_API const char* rtc_version(void);
-/* Run all work of this context on an externally owned cudaStream_t (e.g. torch's current
- * stream), or pass NULL to go back to the context's own stream.                         */
+/* Run all work of this context on an externally owned cudaStream_t (e.g. a torch.cuda.Stream),
+ * or pass NULL to go back to the context's own non-blocking stream.  (NULL never means the
+ * legacy default stream: hand over an explicit stream.)                                   */
 RTC_API int rtc_set_stream(rtc_ctx* ctx, void* cuda_stream);
 RTC_API int rtc_device_info(rtc_ctx* ctx, int* sm_count, int* clock_khz, size_t* smem_optin);
 

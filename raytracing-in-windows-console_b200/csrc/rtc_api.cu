@@ -104,7 +104,7 @@ struct rtc_ctx {
     DevBuf<int32_t> d_hit_idx;
     DevBuf<uint8_t> d_color, d_glyph;
     DevBuf<char> d_out;
-    DevBuf<unsigned long long> d_desc;
+    DevBuf<unsigned char> d_desc;           // encoder scratch: per-tile counts + offsets
     DevBuf<unsigned int> d_counters;        // [0..31] trace tile tickets, [32] encode ticket (never reset)
     DevBuf<unsigned long long> d_total;
     DevBuf<float> d_sink;
@@ -113,7 +113,6 @@ struct rtc_ctx {
     PinBuf<uint8_t> h_color, h_glyph;
     PinBuf<float> h_hit_t;
     PinBuf<int32_t> h_hit_idx;
-    unsigned int enc_ticket_base = 0, enc_epoch = 0;
 
     // last frame
     bool have_frame = false;
@@ -427,14 +426,13 @@ int rtc_render(rtc_ctx* c, const rtc_params* p, rtc_mode mode, uint32_t flags)
     CK(c->d_color.ensure(n_px * mode_bpp(mode) + 16));
     if (mode_has_glyph(mode)) CK(c->d_glyph.ensure(n_px + 16));
     CK(c->d_out.ensure(cap));
-    CK(c->d_desc.ensure(rtc::encode_state_bytes(n_px) / sizeof(unsigned long long)));
+    CK(c->d_desc.ensure(rtc::encode_state_bytes(n_px)));
     c->have_frame = false;
     int rc = trace_shade(c, p, mode, flags, 0, p->y, c->d_color.p, mode_has_glyph(mode) ? c->d_glyph.p : nullptr, true);
     if (rc) return rc;
     CK(rtc::launch_encode(c->stream, c->d_color.p, mode_has_glyph(mode) ? c->d_glyph.p : nullptr, p->x, p->y, mode,
-                          c->d_out.p, cap, c->d_total.p, c->d_desc.p, c->d_counters.p + 32, &c->enc_ticket_base,
-                          &c->enc_epoch));
-    c->last_launches++;
+                          c->d_out.p, cap, c->d_total.p, c->d_desc.p));
+    c->last_launches += 3;
     CK(cudaEventRecord(c->ev[4], c->stream));
     CK(cudaMemcpyAsync(c->h_total.p, c->d_total.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     c->have_frame = true;
@@ -556,9 +554,8 @@ int rtc_encode(rtc_ctx* c, const uint8_t* dev_color, const uint8_t* dev_glyph, u
     if (mode != RTC_SDL && x > 1 && !dev_color) return fail(RTC_ERR_INVALID, "dev_color is NULL");
     if ((uint64_t)(x - 1u) * y >= (1ull << 31)) return fail(RTC_ERR_CAPACITY, "console size too large");
     CK(cudaSetDevice(c->device));
-    CK(c->d_desc.ensure(rtc::encode_state_bytes((uint64_t)(x - 1u) * y) / sizeof(unsigned long long)));
-    CK(rtc::launch_encode(c->stream, dev_color, dev_glyph, x, y, mode, dev_out, cap, dev_total, c->d_desc.p,
-                          c->d_counters.p + 32, &c->enc_ticket_base, &c->enc_epoch));
+    CK(c->d_desc.ensure(rtc::encode_state_bytes((uint64_t)(x - 1u) * y)));
+    CK(rtc::launch_encode(c->stream, dev_color, dev_glyph, x, y, mode, dev_out, cap, dev_total, c->d_desc.p));
     return RTC_OK;
 }
 

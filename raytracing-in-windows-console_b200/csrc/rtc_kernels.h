@@ -31,11 +31,9 @@ cudaError_t launch_shade(cudaStream_t st, const FrameParams& fp, int mode, uint3
 // kernel 3 (rtc_encode.cu)
 cudaError_t configure_encode();
 size_t encode_state_bytes(uint64_t n_cells);
-// `desc`: encode_state_bytes() of device memory (never needs clearing: descriptors are epoch-tagged);
-// `ticket`: one device uint32 that only ever counts up; *ticket_base / *epoch: host-side mirrors.
+// `scratch`: encode_state_bytes() of device memory (per-tile counts and offsets).  Three launches.
 cudaError_t launch_encode(cudaStream_t st, const uint8_t* color, const uint8_t* glyph, uint32_t x, uint32_t y,
-                          int mode, char* out, size_t cap, unsigned long long* total, unsigned long long* desc,
-                          unsigned int* ticket, unsigned int* ticket_base, unsigned int* epoch);
+                          int mode, char* out, size_t cap, unsigned long long* total, void* scratch);
 
 // physics (rtc_shade.cu)
 cudaError_t launch_update_objects(cudaStream_t st, rtc_object* objs, int n, double dt);
