@@ -91,10 +91,6 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def band(y, rank, world):
-    return (y * rank) // world, (y * (rank + 1)) // world
-
-
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_sample(name, mode, seconds, threads=None):
     """Time the reference's own CPU code (oracle/_ref, built from the unmodified sources) on a
@@ -173,7 +169,8 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import rtc_b200
-    from rtc_b200 import scenes
+    from rtc_b200 import multigpu, scenes
+    band = multigpu.band
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -243,19 +240,7 @@ def run_ours(args):
                 dst_c = frame_color[r0 * W * bpp:r1 * W * bpp] if rank == 0 else band_color
                 dst_g = (frame_glyph[r0 * W:r1 * W] if rank == 0 else band_glyph) if has_glyph else None
                 ctx.trace_band(p, mode, r0, r1, dst_c.data_ptr(), dst_g.data_ptr() if has_glyph else 0)
-                ops = []
-                if rank == 0:
-                    for g in range(1, world):
-                        a, b = bands[g]
-                        ops.append(dist.P2POp(dist.irecv, frame_color[a * W * bpp:b * W * bpp], g))
-                        if has_glyph:
-                            ops.append(dist.P2POp(dist.irecv, frame_glyph[a * W:b * W], g))
-                else:
-                    ops.append(dist.P2POp(dist.isend, band_color, 0))
-                    if has_glyph:
-                        ops.append(dist.P2POp(dist.isend, band_glyph, 0))
-                for w in dist.batch_isend_irecv(ops):
-                    w.wait()
+                multigpu.gather_planes(dist, rank, world, y, W, bpp, band_color, frame_color, band_glyph, frame_glyph)
             if rank == 0:
                 ctx.encode(frame_color.data_ptr(), frame_glyph.data_ptr() if has_glyph else 0, x, y, mode,
                            out.data_ptr(), cap, total.data_ptr())

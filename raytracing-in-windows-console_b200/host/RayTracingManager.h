@@ -1,0 +1,41 @@
+// RayTracingManager.h -- THE DROP-IN BOUNDARY, API as the reference's (reference
+// RayTracingManager.h:9-54): per-frame Update(params, objects, dt) that ends in
+// PrintMachine::SetDataInBackBuffer(stream, size).
+#pragma once
+#include <cstddef>
+
+#include "MyMath.h"
+#include "Object3D.h"
+
+struct RayTracingCPUToGPUData
+{
+    MyMath::Matrix inverseVMatrix;
+    MyMath::Vector3 camPos;
+    size_t x;
+    size_t y;
+    float element1;
+    float element2;
+    float camFarDist;
+};
+
+enum RenderingMode { BIT_ASCII = 0, BIT_PIXEL, RGB_ASCII, RGB_PIXEL, RGB_NORMALS, SDL };
+
+class RayTracingManager
+{
+public:
+    RayTracingManager();     // PrintMachine::Start must already have run (reference RayTracingManager.cu:58)
+    ~RayTracingManager();
+
+    void Update(const RayTracingCPUToGPUData& params, const DeviceObjectArray<Object3D*>& objects, double dt);
+    void SetRenderingMode(const RenderingMode newRenderMode);
+
+    // Extensions.  Shadows: opt-in shadow rays (not in the reference).  FixLaunchLimit(true): let
+    // UpdateObjects move more than 1024 objects (the reference's launch is rejected there).
+    void SetShadows(bool on) { m_shadows = on; }
+    void FixLaunchLimit(bool on) { m_fixLaunchLimit = on; }
+
+private:
+    RenderingMode currentRenderingMode = BIT_ASCII;    // reference RayTracingManager.h:53
+    bool m_shadows = false;
+    bool m_fixLaunchLimit = false;
+};

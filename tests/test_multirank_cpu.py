@@ -1,0 +1,70 @@
+"""CPU, world_size 2 and 3 over gloo: the host-side multi-GPU logic (row-band partition, gather of
+the bands to rank 0, one encode over the assembled frame) reproduces the single-rank stream.
+Per-band pixels come from the oracle here (no GPU); the GPU run of the same path is bench.py."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, mode, x, y, out_path):
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import rtc_b200
+    from rtc_b200 import multigpu, scenes
+    from rtc_b200._types import mode_bpp, mode_has_glyph
+    from oracle.oracle import Oracle
+    orc = Oracle()
+    objs = scenes.default_scene()
+    p = rtc_b200.camera_params(x, y, (0, 0, 0), (0, np.float32(np.pi), 0))
+    W, bpp, gl = x - 1, mode_bpp(mode), mode_has_glyph(mode)
+    r0, r1 = multigpu.band(y, rank, world)
+    pl = orc.trace_planes(objs, p, mode, row0=r0, row1=r1, nthreads=1)
+    band_color = torch.from_numpy(pl["color"].copy())
+    band_glyph = torch.from_numpy(pl["glyph"].copy()) if gl else None
+    frame_color = torch.zeros(W * y * bpp, dtype=torch.uint8) if rank == 0 else None
+    frame_glyph = torch.zeros(W * y, dtype=torch.uint8) if (rank == 0 and gl) else None
+    if rank == 0:
+        frame_color[r0 * W * bpp:r1 * W * bpp] = band_color
+        if gl:
+            frame_glyph[r0 * W:r1 * W] = band_glyph
+    multigpu.gather_planes(dist, rank, world, y, W, bpp, band_color, frame_color, band_glyph, frame_glyph)
+    if rank == 0:
+        stream = orc.encode_planes(frame_color.numpy(), frame_glyph.numpy() if gl else None, x, y, mode)
+        np.save(out_path, stream)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,mode,size", [(2, 3, (70, 23)), (3, 2, (41, 10)), (2, 0, (33, 7))])
+def test_rowband_gather_matches_single_rank(tmp_path, oracle, rtc, world, mode, size):
+    x, y = size
+    out = str(tmp_path / "stream.npy")
+    mp.spawn(_worker, args=(world, _free_port(), mode, x, y, out), nprocs=world, join=True)
+    from rtc_b200 import scenes
+    p = rtc.camera_params(x, y, (0, 0, 0), (0, np.float32(np.pi), 0))
+    want = oracle.render(scenes.default_scene(), p, mode)
+    assert np.array_equal(np.load(out), want)
+
+
+def test_band_partition_properties(rtc):
+    from rtc_b200 import multigpu
+    for y in (1, 7, 64, 2160, 4320, 4321):
+        for world in (1, 2, 3, 4, 8):
+            bs = multigpu.bands(y, world)
+            assert bs[0][0] == 0 and bs[-1][1] == y
+            assert all(bs[i][1] == bs[i + 1][0] for i in range(world - 1))          # contiguous, no overlap
+            sizes = [b - a for a, b in bs]
+            assert max(sizes) - min(sizes) <= 1                                      # balanced to one row
