@@ -132,6 +132,33 @@ def cpu_reference_sample(name, mode, seconds, threads=None):
                        % (min(b1 * 16, p.y) - b0 * 16, p.y, b0, b1, name, n_obj, "reference RayTrace_*" if kind == "reference" else "oracle"))
 
 
+def ref_cuda_sample(name, mode, frames=3):
+    """Second reported baseline: the reference's OWN CUDA kernels rebuilt for sm_100 (oracle/_ref/
+    ref_cuda_sm100, compiled from the unmodified sources with the vcxproj's flags)."""
+    import struct
+    import tempfile
+    from rtc_b200 import scenes
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_cuda_sm100")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/ref_cuda_sm100 not built (needs /root/reference at build time)"}
+    objs = scenes.config_scene(name)
+    p = scenes.config_camera(name)
+    with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
+        f.write(struct.pack("<II", len(objs), mode))
+        f.write(bytes(p))
+        f.write(objs.tobytes())
+        path = f.name
+    try:
+        r = subprocess.run([exe, path, str(frames)], capture_output=True, text=True, timeout=300)
+        if r.returncode != 0:
+            return {"unavailable": "ref_cuda_sm100 exited %d: %s" % (r.returncode, (r.stderr or r.stdout)[-200:])}
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:
+        return {"unavailable": repr(e)}
+    finally:
+        os.unlink(path)
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -367,6 +394,7 @@ def run_ours(args):
         line["stages_ms"] = {k: v / args.steps for k, v in stage.items()}
         line["gpu_launches"] = int(launches_per_step * args.steps)
         if not args.no_cpu_baseline:
+            line["ref_cuda_sm100"] = ref_cuda_sample(name, mode)
             try:
                 cb = cpu_reference_sample(name, mode, args.cpu_seconds)
                 line["cpu_baseline"] = {"value": cb["mrays_s"], "unit": "Mrays/s", "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]}
@@ -374,7 +402,7 @@ def run_ours(args):
                 line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
     else:
         # hoist + trace + shade per rank, + encode on rank 0
-        line["gpu_launches"] = int((3 * world + 1) * args.steps)
+        line["gpu_launches"] = int((3 * world + 3) * args.steps)
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
