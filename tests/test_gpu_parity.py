@@ -149,11 +149,12 @@ def test_trace_band_matches_full_frame(ctx, rtc):
 
 def test_encoder_edge_cases(ctx, oracle, rtc):
     """Encoder alone on hand-made planes: ragged sizes, 1-cell rows, long runs, every-cell-differs,
-    tile boundaries (2048-cell tiles), unaligned plane pointers."""
+    slice/tile boundaries (160-cell warp slices, 1280-cell tiles), unaligned plane pointers."""
     import torch
     rng = np.random.default_rng(11)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-    cases = [(2, 1), (2, 9), (3, 3), (18, 5), (2049, 1), (2050, 2), (4097, 3), (700, 37), (1025, 16)]
+    cases = [(2, 1), (2, 9), (3, 3), (5, 2), (6, 7), (18, 5), (161, 1), (162, 3), (321, 7), (1281, 1), (1282, 2), (2049, 1),
+             (2562, 2), (4097, 3), (700, 37), (1025, 16)]
     for (x, y) in cases:
         W = x - 1
         for mode in (RGB_PIXEL, RGB_ASCII, BIT_PIXEL, BIT_ASCII):
