@@ -31,6 +31,10 @@
 #include "rtc_device.cuh"
 #include "rtc_kernels.h"
 
+#ifndef RTC_ENC_BULK_STORE
+#define RTC_ENC_BULK_STORE 1     // slice copy-out by TMA bulk store (cp.async.bulk) instead of a LDS/STG loop
+#endif
+
 namespace rtc {
 
 constexpr int kEncThreads = 256;
@@ -57,20 +61,36 @@ constexpr DigitLut make_digit_lut()
 __device__ const DigitLut d_digit_lut = make_digit_lut();
 
 // ---- per-lane cell analysis, shared by the count and emit passes -------------------------------
+// Exact n / W and n % W for n < 2^31 by one widening multiply: magic = ceil(2^shift / W), shift = 31 + ceil(log2 W)
+// (round-up method: the error magic*W - 2^shift is < W <= 2^(shift-31), so n * error < 2^shift for n < 2^31).
+struct RowDiv { uint32_t W, magic, shift; };
+static RowDiv make_rowdiv(uint32_t W)
+{
+    uint32_t l = 0;
+    while ((1ull << l) < W) ++l;
+    RowDiv d;
+    d.W = W; d.shift = 31u + l;
+    d.magic = (uint32_t)(((1ull << d.shift) + W - 1u) / W);
+    return d;
+}
+__device__ __forceinline__ uint32_t row_col(const RowDiv& d, uint32_t n)
+{
+    const uint32_t q = (uint32_t)(((unsigned long long)n * d.magic) >> d.shift);
+    return n - q * d.W;
+}
+
 // Colour keys of this lane's kEncC cells (key[1..C]) and of the cell before them (key[0]) from aligned
 // 32-bit loads around an arbitrarily aligned plane.  Words outside the plane are never touched.
 template <int BPP>
-__device__ __forceinline__ void load_keys(const uint8_t* __restrict__ color, size_t plane_bytes, uint32_t cell,
+__device__ __forceinline__ void load_keys(const uint8_t* __restrict__ color, uintptr_t first_w, uintptr_t last_w, uintptr_t last_w5, uint32_t cell,
                                           uint32_t (&key)[kEncC + 1])
 {
     constexpr int NIN = BPP == 3 ? 6 : 3;                       // words covering (C+1)*BPP bytes at any phase
-    const uintptr_t base = reinterpret_cast<uintptr_t>(color);
-    const uintptr_t first_w = base & ~(uintptr_t)3, last_w = (base + plane_bytes - 1) & ~(uintptr_t)3;
-    const uintptr_t a = base + (size_t)cell * BPP - BPP;        // predecessor key (garbage for cell 0: unused)
+    const uintptr_t a = reinterpret_cast<uintptr_t>(color) + (size_t)cell * BPP - BPP;   // predecessor key (unused for cell 0)
     const uintptr_t wa = a & ~(uintptr_t)3;
     const uint32_t sh = 8u * (uint32_t)(a & 3u);
     uint32_t w[NIN];
-    if (wa >= first_w && wa + 4u * (NIN - 1) <= last_w) {
+    if (wa >= first_w && wa <= last_w5) {                       // last_w5 = last word of the plane - 4*(NIN-1)
         const uint32_t* p = reinterpret_cast<const uint32_t*>(wa);
 #pragma unroll
         for (int j = 0; j < NIN; ++j) w[j] = __ldg(p + j);
@@ -96,23 +116,43 @@ __device__ __forceinline__ void load_keys(const uint8_t* __restrict__ color, siz
         }
     }
 }
+// Plane bounds for load_keys (word addresses; the plane has at least one byte).
+template <int BPP>
+__device__ __forceinline__ void plane_words(const uint8_t* color, uint32_t n_cells, uintptr_t& first_w, uintptr_t& last_w, uintptr_t& last_w5)
+{
+    constexpr int NIN = BPP == 3 ? 6 : 3;
+    const uintptr_t base = reinterpret_cast<uintptr_t>(color);
+    first_w = base & ~(uintptr_t)3;
+    last_w = (base + (size_t)n_cells * BPP - 1) & ~(uintptr_t)3;
+    // frames smaller than one lane's window always take the clamped path (first_w > last_w5)
+    last_w5 = last_w >= first_w + 4u * (NIN - 1) ? last_w - 4u * (NIN - 1) : first_w - 4u;
+}
 
 // Bit i of full_mask: cell i emits its whole escape sequence; bit i of nl_mask: cell i ends a row.
 // Both restricted to the n_valid leading cells.  Returns the lane's emitted byte count.
 template <int BPP>
-__device__ __forceinline__ uint32_t lane_layout(const uint32_t (&key)[kEncC + 1], uint32_t cell, int n_valid, uint32_t W,
+__device__ __forceinline__ uint32_t lane_layout(const uint32_t (&key)[kEncC + 1], uint32_t cell, int n_valid, const RowDiv& rd,
                                                 uint32_t& full_mask, uint32_t& nl_mask)
 {
     constexpr uint32_t CS = BPP == 3 ? 20u : 12u;               // SIZE_RGB / SIZE_8BIT (RayTracing.h:120-123)
-    uint32_t fm = 0, nm = 0;
-    uint32_t col = cell % W;
+    uint32_t fm = 0;
 #pragma unroll
-    for (int i = 0; i < kEncC; ++i) {
-        const bool differs = key[i + 1] != key[i] || (cell + i == 0u);   // first cell of the frame always emits
-        fm |= differs ? (1u << i) : 0u;
-        const bool nl = col == W - 1u;
-        nm |= nl ? (1u << i) : 0u;
-        col = nl ? 0u : col + 1u;
+    for (int i = 0; i < kEncC; ++i) fm |= (key[i + 1] != key[i]) ? (1u << i) : 0u;
+    fm |= cell == 0u ? 1u : 0u;                                 // first cell of the frame always emits
+    const uint32_t col = row_col(rd, cell);
+    uint32_t nm;
+    if (rd.W >= (uint32_t)kEncC) {                              // at most one row end among 5 consecutive cells
+        const uint32_t d = rd.W - 1u - col;
+        nm = d < (uint32_t)kEncC ? (1u << d) : 0u;
+    } else {                                                    // very narrow consoles
+        nm = 0;
+        uint32_t c = col;
+#pragma unroll
+        for (int i = 0; i < kEncC; ++i) {
+            const bool nl = c == rd.W - 1u;
+            nm |= nl ? (1u << i) : 0u;
+            c = nl ? 0u : c + 1u;
+        }
     }
     const uint32_t vm = (1u << n_valid) - 1u;
     full_mask = fm & vm;
@@ -123,7 +163,7 @@ __device__ __forceinline__ uint32_t lane_layout(const uint32_t (&key)[kEncC + 1]
 // ---- pass 1: per-tile byte counts + per-warp offsets inside the tile ---------------------------
 template <int BPP>
 __global__ void __launch_bounds__(kEncThreads)
-count_kernel(const uint8_t* __restrict__ color, uint32_t W, uint32_t n_cells, uint32_t* __restrict__ tile_len,
+count_kernel(const uint8_t* __restrict__ color, const RowDiv rd, uint32_t n_cells, uint32_t* __restrict__ tile_len,
              uint32_t* __restrict__ warp_excl)
 {
     __shared__ uint32_t s_sum[kEncWarps];
@@ -134,8 +174,10 @@ count_kernel(const uint8_t* __restrict__ color, uint32_t W, uint32_t n_cells, ui
     uint32_t len = 0;
     if (n_valid > 0) {
         uint32_t key[kEncC + 1], fm, nm;
-        load_keys<BPP>(color, (size_t)n_cells * BPP, cell, key);
-        len = lane_layout<BPP>(key, cell, n_valid, W, fm, nm);
+        uintptr_t first_w, last_w, last_w5;
+        plane_words<BPP>(color, n_cells, first_w, last_w, last_w5);
+        load_keys<BPP>(color, first_w, last_w, last_w5, cell, key);
+        len = lane_layout<BPP>(key, cell, n_valid, rd, fm, nm);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) len += __shfl_xor_sync(0xffffffffu, len, o);
@@ -155,7 +197,10 @@ count_kernel(const uint8_t* __restrict__ color, uint32_t W, uint32_t n_cells, ui
 }
 
 // ---- pass 2: exclusive scan of the tile counts (one CTA) ------------------------------------
-constexpr int kScanPerThread = 16;
+// Chunks of 1024 x 16 tiles; a warp owns 512 consecutive tiles and walks them in 16 coalesced rows of 32
+// (loads issued up front), so tile_len is read and tile_off written in whole 128/256-byte lines.
+// A chunk's sum fits 32 bits (16384 tiles x <= 26880 bytes).
+constexpr int kScanRows = 16;
 __global__ void __launch_bounds__(1024)
 scan_kernel(const uint32_t* __restrict__ tile_len, uint32_t n_tiles, unsigned long long* __restrict__ tile_off,
             unsigned long long* __restrict__ total)
@@ -163,22 +208,25 @@ scan_kernel(const uint32_t* __restrict__ tile_len, uint32_t n_tiles, unsigned lo
     __shared__ uint32_t s_warp[32];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     unsigned long long carry = 0ull;
-    // chunks of 1024 x 16 tiles; a chunk's sum fits 32 bits (16384 tiles x <= 26880 bytes)
-    for (uint32_t base = 0; base < n_tiles; base += 1024u * kScanPerThread) {
-        uint32_t v[kScanPerThread];
-        const uint32_t a = base + kScanPerThread * tid;
+    for (uint32_t base = 0; base < n_tiles; base += 1024u * kScanRows) {
+        const uint32_t a = base + warp * (32u * kScanRows) + lane;
+        uint32_t v[kScanRows];
 #pragma unroll
-        for (int k = 0; k < kScanPerThread; ++k) v[k] = (a + k < n_tiles) ? tile_len[a + k] : 0u;
-        uint32_t sum = 0;
+        for (int k = 0; k < kScanRows; ++k) v[k] = (a + 32u * k < n_tiles) ? tile_len[a + 32u * k] : 0u;
+        uint32_t run = 0;                                          // exclusive offset inside the warp's 512 tiles
 #pragma unroll
-        for (int k = 0; k < kScanPerThread; ++k) sum += v[k];
-        uint32_t inc = sum;
+        for (int k = 0; k < kScanRows; ++k) {
+            uint32_t inc = v[k];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= (uint32_t)o) inc += t;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= (uint32_t)o) inc += t;
+            }
+            const uint32_t row_total = __shfl_sync(0xffffffffu, inc, 31);
+            v[k] = run + inc - v[k];
+            run += row_total;
         }
-        if (lane == 31u) s_warp[warp] = inc;
+        if (lane == 0u) s_warp[warp] = run;
         __syncthreads();
         uint32_t wsum = s_warp[lane];                              // every warp scans the 32 warp sums itself
 #pragma unroll
@@ -188,12 +236,10 @@ scan_kernel(const uint32_t* __restrict__ tile_len, uint32_t n_tiles, unsigned lo
         }
         const uint32_t before = __shfl_sync(0xffffffffu, wsum, (warp + 31u) & 31u);   // inclusive sum of warps < warp
         const uint32_t chunk_total = __shfl_sync(0xffffffffu, wsum, 31);
-        unsigned long long run = carry + (warp ? before : 0u) + (inc - sum);
+        const unsigned long long wbase = carry + (warp ? before : 0u);
 #pragma unroll
-        for (int k = 0; k < kScanPerThread; ++k) {
-            if (a + k < n_tiles) tile_off[a + k] = run;
-            run += v[k];
-        }
+        for (int k = 0; k < kScanRows; ++k)
+            if (a + 32u * k < n_tiles) tile_off[a + 32u * k] = wbase + v[k];
         carry += chunk_total;
         __syncthreads();                                           // s_warp is rewritten by the next chunk
     }
@@ -201,14 +247,63 @@ scan_kernel(const uint32_t* __restrict__ tile_len, uint32_t n_tiles, unsigned lo
 }
 
 // ---- pass 3: emit -----------------------------------------------------------------------------
+// One cell into the lane's byte stream.  `acc` holds the last 4 stream bytes, `sel` = 0x7654 - 0x1111*k encodes
+// the k pending (not yet stored) bytes -- the top k bytes of acc -- as the PRMT selector that splices them in
+// front of the next word.
+__device__ __forceinline__ void put_byte(uint32_t*& wp, uint32_t& acc, uint32_t& sel, uint32_t ch)
+{
+    acc = __byte_perm(acc, ch, 0x4321);
+    sel -= 0x1111u;
+    if (sel == 0x3210u) { *wp++ = acc; sel = 0x7654u; }
+}
+
+template <int BPP, bool GLYPH, bool PARTIAL>
+__device__ __forceinline__ void emit_cells(const uint32_t* __restrict__ s_lut, const uint8_t* __restrict__ glyph, uint32_t cell,
+                                           int n_valid, const uint32_t (&key)[kEncC + 1], uint32_t fm, uint32_t nm,
+                                           uint32_t*& wp, uint32_t& acc, uint32_t& sel)
+{
+    constexpr int NWC = BPP == 3 ? 5 : 3;                       // words per full cell
+#pragma unroll
+    for (int i = 0; i < kEncC; ++i) {
+        if (PARTIAL && i >= n_valid) break;
+        const uint32_t g = GLYPH ? (uint32_t)__ldg(glyph + cell + i) : 32u;
+        if ((fm >> i) & 1u) {
+            const uint32_t fg = (GLYPH && g != 32u) ? (uint32_t)'3' : (uint32_t)'4';   // fg for an ASCII-mode hit
+            const uint32_t mch = 'm' | (g << 8);
+            const uint32_t k = key[i + 1];
+            uint32_t c[NWC];
+            c[0] = 0x1bu | ('[' << 8) | (fg << 16) | ('8' << 24);
+            if (BPP == 3) {
+                // ESC [ S 8 | ; 2 ; R2 | R1 R0 ; G2 | G1 G0 ; B2 | B1 B0 m CH   (RayTracing.cu:585-594)
+                const uint32_t lr = s_lut[k & 255u], lg = s_lut[(k >> 8) & 255u], lb = s_lut[k >> 16];
+                c[1] = __byte_perm(';' | ('2' << 8) | (';' << 16), lr, 0x4210);
+                c[2 % NWC] = __byte_perm(lr, lg, 0x4321);
+                c[3 % NWC] = __byte_perm(lg, lb, 0x4321);
+                c[NWC - 1] = __byte_perm(lb, mch, 0x5421);
+            } else {
+                // ESC [ S 8 | ; 5 ; I2 | I1 I0 m CH                              (RayTracing.cu:231-237)
+                const uint32_t li8 = s_lut[k];
+                c[1] = __byte_perm(';' | ('5' << 8) | (';' << 16), li8, 0x4210);
+                c[NWC - 1] = __byte_perm(li8, mch, 0x5421);
+            }
+            wp[0] = __byte_perm(acc, c[0], sel);
+#pragma unroll
+            for (int j = 1; j < NWC; ++j) wp[j] = __byte_perm(c[j - 1], c[j], sel);
+            acc = c[NWC - 1];
+            wp += NWC;
+        } else {
+            put_byte(wp, acc, sel, g);                          // same colour as the previous cell: character only
+        }
+        if ((nm >> i) & 1u) put_byte(wp, acc, sel, (uint32_t)'\n');
+    }
+}
+
 template <int BPP, bool GLYPH>
 __global__ void __launch_bounds__(kEncThreads)
-emit_kernel(const uint8_t* __restrict__ color, const uint8_t* __restrict__ glyph, uint32_t W, uint32_t n_cells,
+emit_kernel(const uint8_t* __restrict__ color, const uint8_t* __restrict__ glyph, const RowDiv rd, uint32_t n_cells,
             char* __restrict__ out, unsigned long long cap, const unsigned long long* __restrict__ tile_off,
             const uint32_t* __restrict__ warp_excl)
 {
-    constexpr int CS = BPP == 3 ? 20 : 12;
-    constexpr int NWC = CS / 4;                                 // words per full cell
     extern __shared__ __align__(16) unsigned char smem[];
     uint32_t* s_lut = reinterpret_cast<uint32_t*>(smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -225,48 +320,14 @@ emit_kernel(const uint8_t* __restrict__ color, const uint8_t* __restrict__ glyph
     const unsigned long long goff = tile_off[tile] + warp_excl[(size_t)tile * kEncWarps + warp];
     unsigned char* stage = smem + 1024 + warp * kEncStageBytes;
 
-    // ---- phase A: keys, lengths, formatted full cells, trailing-bytes shift register ----------
+    // ---- keys, lengths, warp prefix sum --------------------------------------------------------
     uint32_t key[kEncC + 1], fm = 0, nm = 0, len = 0;
     if (n_valid > 0) {
-        load_keys<BPP>(color, (size_t)n_cells * BPP, cell, key);
-        len = lane_layout<BPP>(key, cell, n_valid, W, fm, nm);
+        uintptr_t first_w, last_w, last_w5;
+        plane_words<BPP>(color, n_cells, first_w, last_w, last_w5);
+        load_keys<BPP>(color, first_w, last_w, last_w5, cell, key);
+        len = lane_layout<BPP>(key, cell, n_valid, rd, fm, nm);
     }
-    uint32_t cw[kEncC][NWC];
-    uint32_t gch[kEncC];
-    uint32_t sr = 0;                                            // the last 4 bytes this lane emits
-#pragma unroll
-    for (int i = 0; i < kEncC; ++i) {
-        gch[i] = 32u;
-        if (i < n_valid) {
-            if (GLYPH) gch[i] = (uint32_t)__ldg(glyph + cell + i);
-            if ((fm >> i) & 1u) {
-                const uint32_t g = gch[i];
-                const uint32_t sel = (GLYPH && g != 32u) ? (uint32_t)'3' : (uint32_t)'4';   // fg for an ASCII-mode hit
-                const uint32_t mch = 'm' | (g << 8);
-                const uint32_t k = key[i + 1];
-                cw[i][0] = 0x1bu | ('[' << 8) | (sel << 16) | ('8' << 24);
-                if (BPP == 3) {
-                    // ESC [ S 8 | ; 2 ; R2 | R1 R0 ; G2 | G1 G0 ; B2 | B1 B0 m CH   (RayTracing.cu:585-594)
-                    const uint32_t lr = s_lut[k & 255u], lg = s_lut[(k >> 8) & 255u], lb = s_lut[k >> 16];
-                    cw[i][1] = __byte_perm(';' | ('2' << 8) | (';' << 16), lr, 0x4210);
-                    cw[i][2 % NWC] = __byte_perm(lr, lg, 0x4321);
-                    cw[i][3 % NWC] = __byte_perm(lg, lb, 0x4321);
-                    cw[i][NWC - 1] = __byte_perm(lb, mch, 0x5421);
-                } else {
-                    // ESC [ S 8 | ; 5 ; I2 | I1 I0 m CH                              (RayTracing.cu:231-237)
-                    const uint32_t li8 = s_lut[k];
-                    cw[i][1] = __byte_perm(';' | ('5' << 8) | (';' << 16), li8, 0x4210);
-                    cw[i][NWC - 1] = __byte_perm(li8, mch, 0x5421);
-                }
-                sr = cw[i][NWC - 1];
-            } else {
-                sr = __byte_perm(sr, gch[i], 0x4321);           // same colour as the previous cell: character only
-            }
-            if ((nm >> i) & 1u) sr = __byte_perm(sr, (uint32_t)'\n', 0x4321);
-        }
-    }
-
-    // ---- warp prefix sum of the lane lengths ---------------------------------------------------
     uint32_t inc = len;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -274,41 +335,25 @@ emit_kernel(const uint8_t* __restrict__ color, const uint8_t* __restrict__ glyph
         if (lane >= o) inc += t;
     }
     const uint32_t warp_len = __shfl_sync(0xffffffffu, inc, 31);
-    const uint32_t left_sr = __shfl_up_sync(0xffffffffu, sr, 1);   // lane 0: its own sr, bytes never copied out
 
-    // ---- phase B: stream the cells into the staging image (phase-aligned with the output) ------
+    // ---- stream the cells into the staging image (phase-aligned with the output) ---------------
     const uint32_t out_phase = (uint32_t)(reinterpret_cast<uintptr_t>(out + goff) & 15u);
-    if (n_valid > 0) {
-        const uint32_t pos = out_phase + (inc - len);
-        uint32_t k = pos & 3u;                                  // pending bytes (the top k bytes of acc)
-        uint32_t* wp = reinterpret_cast<uint32_t*>(stage) + (pos >> 2);
-        uint32_t acc = left_sr;
-#pragma unroll
-        for (int i = 0; i < kEncC; ++i) {
-            if (i < n_valid) {
-                if ((fm >> i) & 1u) {
-                    const uint32_t sel = 0x7654u - 0x1111u * k;   // bytes [4-k .. 7-k] of {previous word, this word}
-                    wp[0] = __byte_perm(acc, cw[i][0], sel);
-#pragma unroll
-                    for (int j = 1; j < NWC; ++j) wp[j] = __byte_perm(cw[i][j - 1], cw[i][j], sel);
-                    acc = cw[i][NWC - 1];
-                    wp += NWC;
-                } else {
-                    acc = __byte_perm(acc, gch[i], 0x4321);
-                    if (++k == 4u) { *wp++ = acc; k = 0u; }
-                }
-                if ((nm >> i) & 1u) {
-                    acc = __byte_perm(acc, (uint32_t)'\n', 0x4321);
-                    if (++k == 4u) { *wp++ = acc; k = 0u; }
-                }
-            }
-        }
-        // the slice's last lane flushes its pending bytes itself (everyone else's go to the right neighbour)
-        if (k != 0u && t5 + (uint32_t)n_valid == n_here) *wp = acc >> (8u * (4u - k));
-    }
+    const uint32_t pos = out_phase + (inc - len);
+    const uint32_t k0 = pos & 3u;                               // bytes of my first word that belong to my left neighbour
+    uint32_t* const wp0 = reinterpret_cast<uint32_t*>(stage) + (pos >> 2);
+    uint32_t* wp = wp0;
+    uint32_t acc = 0u, sel = 0x7654u - 0x1111u * k0;
+    if (n_valid == kEncC) emit_cells<BPP, GLYPH, false>(s_lut, glyph, cell, n_valid, key, fm, nm, wp, acc, sel);
+    else if (n_valid > 0) emit_cells<BPP, GLYPH, true>(s_lut, glyph, cell, n_valid, key, fm, nm, wp, acc, sel);
+    // The slice's last lane flushes its pending bytes itself (sel & 7 == 4 - pending) ...
+    if (n_valid > 0 && t5 + (uint32_t)n_valid == n_here && sel != 0x7654u) *wp = acc >> (8u * (sel & 7u));
+    // ... everyone else's complete the first word of the right neighbour (a lane owns >= 5 bytes, so that word
+    // was written -- by the neighbour alone -- with zeros in its low k0 bytes).
+    const uint32_t left = __shfl_up_sync(0xffffffffu, acc, 1);
+    if (lane > 0 && n_valid > 0 && k0 != 0u) *wp0 |= left >> (8u * (4u - k0));
     __syncwarp();
 
-    // ---- copy the slice out: coalesced 128-bit stores -------------------------------------
+    // ---- copy the slice out ---------------------------------------------------------------------
     if (goff >= cap) return;
     const uint32_t n_out = (uint32_t)min((unsigned long long)warp_len, cap - goff);
     char* dst = out + goff;
@@ -316,11 +361,26 @@ emit_kernel(const uint8_t* __restrict__ color, const uint8_t* __restrict__ glyph
     const uint32_t head = out_phase ? min(16u - out_phase, n_out) : 0u;
     if ((uint32_t)lane < head) dst[lane] = (char)src[lane];
     const uint32_t nvec = (n_out - head) >> 4;
+#if RTC_ENC_BULK_STORE
+    // TMA bulk store of the 16-byte aligned body: one instruction instead of a LDS.128/STG.128 loop.
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0 && nvec) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     :: "l"(dst + head), "r"((uint32_t)__cvta_generic_to_shared(src + head)), "r"(nvec << 4) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+#else
     uint4* vdst = reinterpret_cast<uint4*>(dst + head);
     const uint4* vsrc = reinterpret_cast<const uint4*>(src + head);
+#pragma unroll 1
     for (uint32_t i = lane; i < nvec; i += 32u) vdst[i] = vsrc[i];
+#endif
     const uint32_t done = head + (nvec << 4);
     if ((uint32_t)lane < n_out - done) dst[done + lane] = (char)src[done + lane];
+#if RTC_ENC_BULK_STORE
+    if (lane == 0 && nvec) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must outlive the read
+#endif
 }
 
 // SDL mode (reference RayTrace_SDL writes nothing, RayTracing.cu:755-795): y newlines.
@@ -372,12 +432,13 @@ cudaError_t launch_encode(cudaStream_t st, const uint8_t* color, const uint8_t* 
     uint32_t* warp_excl = tile_len + n_tiles + 1;
     const bool has_glyph = (mode == RTC_BIT_ASCII || mode == RTC_RGB_ASCII) && glyph != nullptr;
     const bool bit8 = (mode == RTC_BIT_ASCII || mode == RTC_BIT_PIXEL);
-    if (bit8) count_kernel<1><<<n_tiles, kEncThreads, 0, st>>>(color, W, n_cells, tile_len, warp_excl);
-    else count_kernel<3><<<n_tiles, kEncThreads, 0, st>>>(color, W, n_cells, tile_len, warp_excl);
+    const RowDiv rd = make_rowdiv(W);
+    if (bit8) count_kernel<1><<<n_tiles, kEncThreads, 0, st>>>(color, rd, n_cells, tile_len, warp_excl);
+    else count_kernel<3><<<n_tiles, kEncThreads, 0, st>>>(color, rd, n_cells, tile_len, warp_excl);
     scan_kernel<<<1, 1024, 0, st>>>(tile_len, n_tiles, tile_off, total);
 #define RTC_LAUNCH_ENC(BPP, GL)                                                                         \
     emit_kernel<BPP, GL><<<n_tiles, kEncThreads, enc_smem(), st>>>(                                     \
-        color, glyph, W, n_cells, out, (unsigned long long)cap, tile_off, warp_excl)
+        color, glyph, rd, n_cells, out, (unsigned long long)cap, tile_off, warp_excl)
     if (bit8) { if (has_glyph) RTC_LAUNCH_ENC(1, true); else RTC_LAUNCH_ENC(1, false); }
     else      { if (has_glyph) RTC_LAUNCH_ENC(3, true); else RTC_LAUNCH_ENC(3, false); }
 #undef RTC_LAUNCH_ENC
