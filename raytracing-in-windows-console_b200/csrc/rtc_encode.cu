@@ -12,9 +12,12 @@
 //         character; one '\n' after each row.  (Proven byte-identical to the reference's scan
 //         by tests)
 //
-// Three launches, no inter-CTA waiting:
-//   1. count : a lane owns 5 CONSECUTIVE cells, a warp 160, a CTA (8 warps) one tile of 1280; writes the
-//              tile's emitted byte count and the exclusive offset of each of its 8 warp slices;
+// Three launches, no inter-CTA waiting (a fused single-pass version with decoupled look-back -- per slice, per
+// tile, and two-level -- was measured at 0.32-0.44 ms against 0.18 ms: with the store stream saturating HBM the
+// descriptor round trips are exposed; the same kernel with the look-back skipped ran in 0.152 ms.  Kept under
+// scripts/experiments/; numbers in profiles/r01_encode_history.md):
+//   1. count : a tile is 1280 cells = 8 warp slices of 160; writes the tile's emitted byte count and the
+//              exclusive offset of each of its 8 slices (a lane counts 20 consecutive cells here);
 //   2. scan  : one CTA turns the tile counts into exclusive 64-bit offsets + the stream length;
 //   3. emit  : every WARP is autonomous (no CTA barrier after the LUT is staged): it re-derives its
 //              lanes' lengths, prefix-sums them with shuffles, and each lane streams its cells through a
@@ -23,17 +26,14 @@
 //              a whole aligned STS.32 -- a lane's leading partial word is completed with the trailing
 //              bytes of its left neighbour, passed by one shuffle (a lane always owns >= 5 bytes, so a
 //              word never spans three lanes).  5 cells per lane makes the lane stride odd (25 / 15 words
-//              when every cell is full, the worst case), hence bank-conflict free.  The slice is then
-//              copied out with coalesced 128-bit stores, phase-aligned with the global offset.
+//              when every cell is full, the worst case), hence bank-conflict free.  The slice then leaves
+//              through ONE TMA bulk store (cp.async.bulk shared -> global; the image is phase-aligned with the
+//              global offset) plus <= 15 head and tail bytes.
 // Algorithmic traffic: BPP (+1) bytes read and the emitted bytes written per cell.
 // (r01a design -- 4 lane-strided cells per thread, byte-granular predicated stores, 3 CTA barriers -- cost
 // 198 thread instructions per cell and was issue-bound at 30 % of HBM peak: profiles/r01a_encode_3pass_ncu.md.)
 #include "rtc_device.cuh"
 #include "rtc_kernels.h"
-
-#ifndef RTC_ENC_BULK_STORE
-#define RTC_ENC_BULK_STORE 1     // slice copy-out by TMA bulk store (cp.async.bulk) instead of a LDS/STG loop
-#endif
 
 namespace rtc {
 
@@ -60,37 +60,44 @@ constexpr DigitLut make_digit_lut()
 }
 __device__ const DigitLut d_digit_lut = make_digit_lut();
 
-// ---- per-lane cell analysis, shared by the count and emit passes -------------------------------
-// Exact n / W and n % W for n < 2^31 by one widening multiply: magic = ceil(2^shift / W), shift = 31 + ceil(log2 W)
-// (round-up method: the error magic*W - 2^shift is < W <= 2^(shift-31), so n * error < 2^shift for n < 2^31).
-struct RowDiv { uint32_t W, magic, shift; };
-static RowDiv make_rowdiv(uint32_t W)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)   // PRMT without __byte_perm's selector mask
 {
-    uint32_t l = 0;
-    while ((1ull << l) < W) ++l;
-    RowDiv d;
-    d.W = W; d.shift = 31u + l;
-    d.magic = (uint32_t)(((1ull << d.shift) + W - 1u) / W);
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
     return d;
 }
-__device__ __forceinline__ uint32_t row_col(const RowDiv& d, uint32_t n)
+
+// ---- per-lane cell analysis, shared by the count and emit passes -------------------------------
+// Launch-invariant geometry, computed once on the host.
+struct EncGeom {
+    uint32_t W, magic, shift;        // exact n / W for n < 2^31 by one widening multiply (round-up method:
+                                     // magic = ceil(2^shift / W), shift = 31 + ceil(log2 W); the error magic*W - 2^shift
+                                     // is < W <= 2^(shift-31), so n * error < 2^shift for every n < 2^31)
+    uint32_t n_cells;
+    uint32_t fast_hi_emit, fast_hi_count;   // lanes with cell-1 < fast_hi may load their key window unclamped
+    unsigned long long first_w, last_w;     // first / last 32-bit word holding plane bytes
+};
+template <int BPP, int C> struct EncIn {
+    static constexpr int NIN = ((C + 1) * BPP + 3) / 4 + 1;                // aligned words of key bytes + 1 for the phase
+    static constexpr int MARGIN = (4 * NIN - BPP + BPP - 1) / BPP;         // cell + MARGIN <= n_cells: window inside the plane
+};
+__device__ __forceinline__ uint32_t row_of(const EncGeom& g, uint32_t n)
 {
-    const uint32_t q = (uint32_t)(((unsigned long long)n * d.magic) >> d.shift);
-    return n - q * d.W;
+    return (uint32_t)(((unsigned long long)n * g.magic) >> g.shift);
 }
 
-// Colour keys of this lane's kEncC cells (key[1..C]) and of the cell before them (key[0]) from aligned
+// Colour keys of this lane's C consecutive cells (key[1..C]) and of the cell before them (key[0]) from aligned
 // 32-bit loads around an arbitrarily aligned plane.  Words outside the plane are never touched.
-template <int BPP>
-__device__ __forceinline__ void load_keys(const uint8_t* __restrict__ color, uintptr_t first_w, uintptr_t last_w, uintptr_t last_w5, uint32_t cell,
-                                          uint32_t (&key)[kEncC + 1])
+template <int BPP, int C>
+__device__ __forceinline__ void load_keys(const uint8_t* __restrict__ color, const EncGeom& g, uint32_t fast_hi, uint32_t cell,
+                                          uint32_t (&key)[C + 1])
 {
-    constexpr int NIN = BPP == 3 ? 6 : 3;                       // words covering (C+1)*BPP bytes at any phase
+    constexpr int NIN = EncIn<BPP, C>::NIN;
     const uintptr_t a = reinterpret_cast<uintptr_t>(color) + (size_t)cell * BPP - BPP;   // predecessor key (unused for cell 0)
     const uintptr_t wa = a & ~(uintptr_t)3;
     const uint32_t sh = 8u * (uint32_t)(a & 3u);
     uint32_t w[NIN];
-    if (wa >= first_w && wa <= last_w5) {                       // last_w5 = last word of the plane - 4*(NIN-1)
+    if (cell - 1u < fast_hi) {
         const uint32_t* p = reinterpret_cast<const uint32_t*>(wa);
 #pragma unroll
         for (int j = 0; j < NIN; ++j) w[j] = __ldg(p + j);
@@ -98,8 +105,8 @@ __device__ __forceinline__ void load_keys(const uint8_t* __restrict__ color, uin
 #pragma unroll
         for (int j = 0; j < NIN; ++j) {
             uintptr_t q = wa + 4u * j;
-            q = q < first_w ? first_w : q;
-            q = q > last_w ? last_w : q;
+            q = q < (uintptr_t)g.first_w ? (uintptr_t)g.first_w : q;
+            q = q > (uintptr_t)g.last_w ? (uintptr_t)g.last_w : q;
             w[j] = __ldg(reinterpret_cast<const uint32_t*>(q));
         }
     }
@@ -107,7 +114,7 @@ __device__ __forceinline__ void load_keys(const uint8_t* __restrict__ color, uin
 #pragma unroll
     for (int j = 0; j < NIN - 1; ++j) A[j] = __funnelshift_r(w[j], w[j + 1], sh);
 #pragma unroll
-    for (int i = 0; i <= kEncC; ++i) {
+    for (int i = 0; i <= C; ++i) {
         if (BPP == 3) {
             const int off = 3 * i, wd = off >> 2, s = off & 3;
             key[i] = s == 0 ? (A[wd] & 0xffffffu) : s == 1 ? (A[wd] >> 8) : (__funnelshift_r(A[wd], A[wd + 1], 8 * s) & 0xffffffu);
@@ -116,91 +123,69 @@ __device__ __forceinline__ void load_keys(const uint8_t* __restrict__ color, uin
         }
     }
 }
-// Plane bounds for load_keys (word addresses; the plane has at least one byte).
-template <int BPP>
-__device__ __forceinline__ void plane_words(const uint8_t* color, uint32_t n_cells, uintptr_t& first_w, uintptr_t& last_w, uintptr_t& last_w5)
-{
-    constexpr int NIN = BPP == 3 ? 6 : 3;
-    const uintptr_t base = reinterpret_cast<uintptr_t>(color);
-    first_w = base & ~(uintptr_t)3;
-    last_w = (base + (size_t)n_cells * BPP - 1) & ~(uintptr_t)3;
-    // frames smaller than one lane's window always take the clamped path (first_w > last_w5)
-    last_w5 = last_w >= first_w + 4u * (NIN - 1) ? last_w - 4u * (NIN - 1) : first_w - 4u;
-}
 
-// Bit i of full_mask: cell i emits its whole escape sequence; bit i of nl_mask: cell i ends a row.
-// Both restricted to the n_valid leading cells.  Returns the lane's emitted byte count.
-template <int BPP>
-__device__ __forceinline__ uint32_t lane_layout(const uint32_t (&key)[kEncC + 1], uint32_t cell, int n_valid, const RowDiv& rd,
-                                                uint32_t& full_mask, uint32_t& nl_mask)
+// Bit i of the result: cell i emits its whole escape sequence (its colour key differs from its predecessor's).
+template <int C>
+__device__ __forceinline__ uint32_t full_cells(const uint32_t (&key)[C + 1], uint32_t cell, int n_valid)
 {
-    constexpr uint32_t CS = BPP == 3 ? 20u : 12u;               // SIZE_RGB / SIZE_8BIT (RayTracing.h:120-123)
     uint32_t fm = 0;
 #pragma unroll
-    for (int i = 0; i < kEncC; ++i) fm |= (key[i + 1] != key[i]) ? (1u << i) : 0u;
+    for (int i = 0; i < C; ++i) fm |= (key[i + 1] != key[i]) ? (1u << i) : 0u;
     fm |= cell == 0u ? 1u : 0u;                                 // first cell of the frame always emits
-    const uint32_t col = row_col(rd, cell);
-    uint32_t nm;
-    if (rd.W >= (uint32_t)kEncC) {                              // at most one row end among 5 consecutive cells
-        const uint32_t d = rd.W - 1u - col;
-        nm = d < (uint32_t)kEncC ? (1u << d) : 0u;
-    } else {                                                    // very narrow consoles
-        nm = 0;
-        uint32_t c = col;
-#pragma unroll
-        for (int i = 0; i < kEncC; ++i) {
-            const bool nl = c == rd.W - 1u;
-            nm |= nl ? (1u << i) : 0u;
-            c = nl ? 0u : c + 1u;
-        }
-    }
-    const uint32_t vm = (1u << n_valid) - 1u;
-    full_mask = fm & vm;
-    nl_mask = nm & vm;
-    return (uint32_t)n_valid + (CS - 1u) * __popc(full_mask) + __popc(nl_mask);
+    return fm & ((1u << n_valid) - 1u);
 }
 
-// ---- pass 1: per-tile byte counts + per-warp offsets inside the tile ---------------------------
+// ---- pass 1: per-tile byte counts + per-slice offsets inside the tile ---------------------------
+// Counting does not need the emit pass's 5-cells-per-lane layout, only its slice boundaries: here a lane owns
+// kCntC = 20 consecutive cells (8 lanes per 160-cell slice, 4 slices per warp, 4 tiles per CTA), which
+// amortises the address arithmetic over 4x the cells.
+constexpr int kCntC = 4 * kEncC;
+constexpr int kCntTiles = kEncThreads * kCntC / kEncTile;      // tiles per count CTA
+static_assert(kCntC * 8 == kEncWarpCells && kCntTiles * kEncTile == kEncThreads * kCntC, "count layout");
 template <int BPP>
 __global__ void __launch_bounds__(kEncThreads)
-count_kernel(const uint8_t* __restrict__ color, const RowDiv rd, uint32_t n_cells, uint32_t* __restrict__ tile_len,
-             uint32_t* __restrict__ warp_excl)
+count_kernel(const uint8_t* __restrict__ color, const EncGeom g, uint32_t* __restrict__ tile_len, uint32_t* __restrict__ warp_excl)
 {
-    __shared__ uint32_t s_sum[kEncWarps];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t tile = blockIdx.x;
-    const uint32_t cell = tile * (uint32_t)kEncTile + (uint32_t)warp * kEncWarpCells + (uint32_t)lane * kEncC;
-    const int n_valid = cell >= n_cells ? 0 : (int)min((uint32_t)kEncC, n_cells - cell);
+    constexpr uint32_t CS = BPP == 3 ? 20u : 12u;               // SIZE_RGB / SIZE_8BIT (RayTracing.h:120-123)
+    __shared__ uint32_t s_len[kEncThreads / 8];                 // one per slice
+    const int tid = threadIdx.x;
+    const uint32_t cell = (blockIdx.x * (uint32_t)kEncThreads + (uint32_t)tid) * kCntC;
+    const int n_valid = cell >= g.n_cells ? 0 : (int)min((uint32_t)kCntC, g.n_cells - cell);
     uint32_t len = 0;
     if (n_valid > 0) {
-        uint32_t key[kEncC + 1], fm, nm;
-        uintptr_t first_w, last_w, last_w5;
-        plane_words<BPP>(color, n_cells, first_w, last_w, last_w5);
-        load_keys<BPP>(color, first_w, last_w, last_w5, cell, key);
-        len = lane_layout<BPP>(key, cell, n_valid, rd, fm, nm);
+        uint32_t key[kCntC + 1];
+        load_keys<BPP, kCntC>(color, g, g.fast_hi_count, cell, key);
+        const uint32_t fm = full_cells<kCntC>(key, cell, n_valid);
+        const uint32_t newlines = row_of(g, cell + (uint32_t)n_valid) - row_of(g, cell);   // row ends in [cell, cell + n_valid)
+        len = (uint32_t)n_valid + (CS - 1u) * __popc(fm) + newlines;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) len += __shfl_xor_sync(0xffffffffu, len, o);
-    if (lane == 0) s_sum[warp] = len;
+    len += __shfl_xor_sync(0xffffffffu, len, 1);
+    len += __shfl_xor_sync(0xffffffffu, len, 2);
+    len += __shfl_xor_sync(0xffffffffu, len, 4);
+    if ((tid & 7) == 0) s_len[tid >> 3] = len;
     __syncthreads();
-    if (tid < kEncWarps) {
-        uint32_t excl = 0, tot = 0;
+    if (tid < kEncThreads / 8) {                                // one thread per slice
+        const uint32_t tile = blockIdx.x * (uint32_t)kCntTiles + ((uint32_t)tid >> 3);
+        if ((uint64_t)tile * kEncTile < g.n_cells) {
+            const int s0 = tid & ~7;
+            uint32_t excl = 0, tot = 0;
 #pragma unroll
-        for (int w = 0; w < kEncWarps; ++w) {
-            const uint32_t v = s_sum[w];
-            excl += w < tid ? v : 0u;
-            tot += v;
+            for (int w = 0; w < kEncWarps; ++w) {
+                const uint32_t v = s_len[s0 + w];
+                excl += w < (tid & 7) ? v : 0u;
+                tot += v;
+            }
+            warp_excl[(size_t)tile * kEncWarps + (tid & 7)] = excl;
+            if ((tid & 7) == 0) tile_len[tile] = tot;
         }
-        warp_excl[(size_t)tile * kEncWarps + tid] = excl;
-        if (tid == 0) tile_len[tile] = tot;
     }
 }
 
 // ---- pass 2: exclusive scan of the tile counts (one CTA) ------------------------------------
-// Chunks of 1024 x 16 tiles; a warp owns 512 consecutive tiles and walks them in 16 coalesced rows of 32
-// (loads issued up front), so tile_len is read and tile_off written in whole 128/256-byte lines.
-// A chunk's sum fits 32 bits (16384 tiles x <= 26880 bytes).
-constexpr int kScanRows = 16;
+// Chunks of 1024 x 32 tiles (one chunk up to 8K frames); a warp owns 1024 consecutive tiles and walks them in 32
+// coalesced rows of 32 (loads issued up front), so tile_len is read and tile_off written in whole lines.
+// A chunk's sum fits 32 bits (32768 tiles x <= 26880 bytes).
+constexpr int kScanRows = 32;
 __global__ void __launch_bounds__(1024)
 scan_kernel(const uint32_t* __restrict__ tile_len, uint32_t n_tiles, unsigned long long* __restrict__ tile_off,
             unsigned long long* __restrict__ total)
@@ -213,7 +198,7 @@ scan_kernel(const uint32_t* __restrict__ tile_len, uint32_t n_tiles, unsigned lo
         uint32_t v[kScanRows];
 #pragma unroll
         for (int k = 0; k < kScanRows; ++k) v[k] = (a + 32u * k < n_tiles) ? tile_len[a + 32u * k] : 0u;
-        uint32_t run = 0;                                          // exclusive offset inside the warp's 512 tiles
+        uint32_t run = 0;                                          // exclusive offset inside the warp's tiles
 #pragma unroll
         for (int k = 0; k < kScanRows; ++k) {
             uint32_t inc = v[k];
@@ -252,12 +237,13 @@ scan_kernel(const uint32_t* __restrict__ tile_len, uint32_t n_tiles, unsigned lo
 // front of the next word.
 __device__ __forceinline__ void put_byte(uint32_t*& wp, uint32_t& acc, uint32_t& sel, uint32_t ch)
 {
-    acc = __byte_perm(acc, ch, 0x4321);
+    acc = prmt(acc, ch, 0x4321u);
     sel -= 0x1111u;
     if (sel == 0x3210u) { *wp++ = acc; sel = 0x7654u; }
 }
 
-template <int BPP, bool GLYPH, bool PARTIAL>
+// SLOW: lanes with fewer than kEncC valid cells or with a row end among their cells.
+template <int BPP, bool GLYPH, bool SLOW>
 __device__ __forceinline__ void emit_cells(const uint32_t* __restrict__ s_lut, const uint8_t* __restrict__ glyph, uint32_t cell,
                                            int n_valid, const uint32_t (&key)[kEncC + 1], uint32_t fm, uint32_t nm,
                                            uint32_t*& wp, uint32_t& acc, uint32_t& sel)
@@ -265,7 +251,7 @@ __device__ __forceinline__ void emit_cells(const uint32_t* __restrict__ s_lut, c
     constexpr int NWC = BPP == 3 ? 5 : 3;                       // words per full cell
 #pragma unroll
     for (int i = 0; i < kEncC; ++i) {
-        if (PARTIAL && i >= n_valid) break;
+        if (SLOW && i >= n_valid) break;
         const uint32_t g = GLYPH ? (uint32_t)__ldg(glyph + cell + i) : 32u;
         if ((fm >> i) & 1u) {
             const uint32_t fg = (GLYPH && g != 32u) ? (uint32_t)'3' : (uint32_t)'4';   // fg for an ASCII-mode hit
@@ -276,34 +262,35 @@ __device__ __forceinline__ void emit_cells(const uint32_t* __restrict__ s_lut, c
             if (BPP == 3) {
                 // ESC [ S 8 | ; 2 ; R2 | R1 R0 ; G2 | G1 G0 ; B2 | B1 B0 m CH   (RayTracing.cu:585-594)
                 const uint32_t lr = s_lut[k & 255u], lg = s_lut[(k >> 8) & 255u], lb = s_lut[k >> 16];
-                c[1] = __byte_perm(';' | ('2' << 8) | (';' << 16), lr, 0x4210);
-                c[2 % NWC] = __byte_perm(lr, lg, 0x4321);
-                c[3 % NWC] = __byte_perm(lg, lb, 0x4321);
-                c[NWC - 1] = __byte_perm(lb, mch, 0x5421);
+                c[1] = prmt(';' | ('2' << 8) | (';' << 16), lr, 0x4210u);
+                c[2 % NWC] = prmt(lr, lg, 0x4321u);
+                c[3 % NWC] = prmt(lg, lb, 0x4321u);
+                c[NWC - 1] = prmt(lb, mch, 0x5421u);
             } else {
                 // ESC [ S 8 | ; 5 ; I2 | I1 I0 m CH                              (RayTracing.cu:231-237)
                 const uint32_t li8 = s_lut[k];
-                c[1] = __byte_perm(';' | ('5' << 8) | (';' << 16), li8, 0x4210);
-                c[NWC - 1] = __byte_perm(li8, mch, 0x5421);
+                c[1] = prmt(';' | ('5' << 8) | (';' << 16), li8, 0x4210u);
+                c[NWC - 1] = prmt(li8, mch, 0x5421u);
             }
-            wp[0] = __byte_perm(acc, c[0], sel);
+            wp[0] = prmt(acc, c[0], sel);
 #pragma unroll
-            for (int j = 1; j < NWC; ++j) wp[j] = __byte_perm(c[j - 1], c[j], sel);
+            for (int j = 1; j < NWC; ++j) wp[j] = prmt(c[j - 1], c[j], sel);
             acc = c[NWC - 1];
             wp += NWC;
         } else {
             put_byte(wp, acc, sel, g);                          // same colour as the previous cell: character only
         }
-        if ((nm >> i) & 1u) put_byte(wp, acc, sel, (uint32_t)'\n');
+        if (SLOW && ((nm >> i) & 1u)) put_byte(wp, acc, sel, (uint32_t)'\n');
     }
 }
 
 template <int BPP, bool GLYPH>
 __global__ void __launch_bounds__(kEncThreads)
-emit_kernel(const uint8_t* __restrict__ color, const uint8_t* __restrict__ glyph, const RowDiv rd, uint32_t n_cells,
+emit_kernel(const uint8_t* __restrict__ color, const uint8_t* __restrict__ glyph, const EncGeom g,
             char* __restrict__ out, unsigned long long cap, const unsigned long long* __restrict__ tile_off,
             const uint32_t* __restrict__ warp_excl)
 {
+    constexpr uint32_t CS = BPP == 3 ? 20u : 12u;
     extern __shared__ __align__(16) unsigned char smem[];
     uint32_t* s_lut = reinterpret_cast<uint32_t*>(smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -312,8 +299,8 @@ emit_kernel(const uint8_t* __restrict__ color, const uint8_t* __restrict__ glyph
 
     const uint32_t tile = blockIdx.x;
     const uint32_t cell_w0 = tile * (uint32_t)kEncTile + (uint32_t)warp * kEncWarpCells;
-    if (cell_w0 >= n_cells) return;                             // warp-uniform
-    const uint32_t n_here = min((uint32_t)kEncWarpCells, n_cells - cell_w0);
+    if (cell_w0 >= g.n_cells) return;                           // warp-uniform
+    const uint32_t n_here = min((uint32_t)kEncWarpCells, g.n_cells - cell_w0);
     const uint32_t t5 = (uint32_t)lane * kEncC;
     const uint32_t cell = cell_w0 + t5;
     const int n_valid = t5 >= n_here ? 0 : (int)min((uint32_t)kEncC, n_here - t5);
@@ -323,10 +310,23 @@ emit_kernel(const uint8_t* __restrict__ color, const uint8_t* __restrict__ glyph
     // ---- keys, lengths, warp prefix sum --------------------------------------------------------
     uint32_t key[kEncC + 1], fm = 0, nm = 0, len = 0;
     if (n_valid > 0) {
-        uintptr_t first_w, last_w, last_w5;
-        plane_words<BPP>(color, n_cells, first_w, last_w, last_w5);
-        load_keys<BPP>(color, first_w, last_w, last_w5, cell, key);
-        len = lane_layout<BPP>(key, cell, n_valid, rd, fm, nm);
+        load_keys<BPP, kEncC>(color, g, g.fast_hi_emit, cell, key);
+        fm = full_cells<kEncC>(key, cell, n_valid);
+        const uint32_t col = cell - row_of(g, cell) * g.W;
+        if (g.W >= (uint32_t)kEncC) {                           // at most one row end among kEncC consecutive cells
+            const uint32_t d = g.W - 1u - col;
+            nm = d < (uint32_t)kEncC ? (1u << d) : 0u;
+        } else {                                                // very narrow consoles
+            uint32_t c = col;
+#pragma unroll
+            for (int i = 0; i < kEncC; ++i) {
+                const bool nl = c == g.W - 1u;
+                nm |= nl ? (1u << i) : 0u;
+                c = nl ? 0u : c + 1u;
+            }
+        }
+        nm &= (1u << n_valid) - 1u;
+        len = (uint32_t)n_valid + (CS - 1u) * __popc(fm) + __popc(nm);
     }
     uint32_t inc = len;
 #pragma unroll
@@ -343,7 +343,7 @@ emit_kernel(const uint8_t* __restrict__ color, const uint8_t* __restrict__ glyph
     uint32_t* const wp0 = reinterpret_cast<uint32_t*>(stage) + (pos >> 2);
     uint32_t* wp = wp0;
     uint32_t acc = 0u, sel = 0x7654u - 0x1111u * k0;
-    if (n_valid == kEncC) emit_cells<BPP, GLYPH, false>(s_lut, glyph, cell, n_valid, key, fm, nm, wp, acc, sel);
+    if (n_valid == kEncC && nm == 0u) emit_cells<BPP, GLYPH, false>(s_lut, glyph, cell, n_valid, key, fm, nm, wp, acc, sel);
     else if (n_valid > 0) emit_cells<BPP, GLYPH, true>(s_lut, glyph, cell, n_valid, key, fm, nm, wp, acc, sel);
     // The slice's last lane flushes its pending bytes itself (sel & 7 == 4 - pending) ...
     if (n_valid > 0 && t5 + (uint32_t)n_valid == n_here && sel != 0x7654u) *wp = acc >> (8u * (sel & 7u));
@@ -351,36 +351,43 @@ emit_kernel(const uint8_t* __restrict__ color, const uint8_t* __restrict__ glyph
     // was written -- by the neighbour alone -- with zeros in its low k0 bytes).
     const uint32_t left = __shfl_up_sync(0xffffffffu, acc, 1);
     if (lane > 0 && n_valid > 0 && k0 != 0u) *wp0 |= left >> (8u * (4u - k0));
-    __syncwarp();
 
-    // ---- copy the slice out ---------------------------------------------------------------------
+    // ---- copy the slice out: head bytes, one TMA bulk store of the 16-byte aligned body, tail bytes ---------
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy STS -> visible to the async proxy
+    __syncwarp();
     if (goff >= cap) return;
     const uint32_t n_out = (uint32_t)min((unsigned long long)warp_len, cap - goff);
     char* dst = out + goff;
     const unsigned char* src = stage + out_phase;
     const uint32_t head = out_phase ? min(16u - out_phase, n_out) : 0u;
-    if ((uint32_t)lane < head) dst[lane] = (char)src[lane];
-    const uint32_t nvec = (n_out - head) >> 4;
-#if RTC_ENC_BULK_STORE
-    // TMA bulk store of the 16-byte aligned body: one instruction instead of a LDS.128/STG.128 loop.
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncwarp();
-    if (lane == 0 && nvec) {
+    const uint32_t body = (n_out - head) & ~15u;
+    if (lane == 0 && body) {
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                     :: "l"(dst + head), "r"((uint32_t)__cvta_generic_to_shared(src + head)), "r"(nvec << 4) : "memory");
+                     :: "l"(dst + head), "r"((uint32_t)__cvta_generic_to_shared(src + head)), "r"(body) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
-#else
-    uint4* vdst = reinterpret_cast<uint4*>(dst + head);
-    const uint4* vsrc = reinterpret_cast<const uint4*>(src + head);
-#pragma unroll 1
-    for (uint32_t i = lane; i < nvec; i += 32u) vdst[i] = vsrc[i];
-#endif
-    const uint32_t done = head + (nvec << 4);
+    if ((uint32_t)lane < head) dst[lane] = (char)src[lane];
+    const uint32_t done = head + body;
     if ((uint32_t)lane < n_out - done) dst[done + lane] = (char)src[done + lane];
-#if RTC_ENC_BULK_STORE
-    if (lane == 0 && nvec) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must outlive the read
-#endif
+    if (lane == 0 && body) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must outlive the read
+}
+
+template <int BPP>
+static EncGeom make_geom(const uint8_t* color, uint32_t W, uint32_t n_cells)
+{
+    EncGeom g;
+    uint32_t l = 0;
+    while ((1ull << l) < W) ++l;
+    g.W = W; g.shift = 31u + l;
+    g.magic = (uint32_t)(((1ull << g.shift) + W - 1u) / W);
+    g.n_cells = n_cells;
+    const uint32_t me = (uint32_t)EncIn<BPP, kEncC>::MARGIN, mc = (uint32_t)EncIn<BPP, kCntC>::MARGIN;
+    g.fast_hi_emit = n_cells >= me ? n_cells - me : 0u;
+    g.fast_hi_count = n_cells >= mc ? n_cells - mc : 0u;
+    const unsigned long long base = (unsigned long long)reinterpret_cast<uintptr_t>(color);
+    g.first_w = base & ~3ull;
+    g.last_w = (base + (unsigned long long)n_cells * BPP - 1ull) & ~3ull;
+    return g;
 }
 
 // SDL mode (reference RayTrace_SDL writes nothing, RayTracing.cu:755-795): y newlines.
@@ -432,13 +439,14 @@ cudaError_t launch_encode(cudaStream_t st, const uint8_t* color, const uint8_t* 
     uint32_t* warp_excl = tile_len + n_tiles + 1;
     const bool has_glyph = (mode == RTC_BIT_ASCII || mode == RTC_RGB_ASCII) && glyph != nullptr;
     const bool bit8 = (mode == RTC_BIT_ASCII || mode == RTC_BIT_PIXEL);
-    const RowDiv rd = make_rowdiv(W);
-    if (bit8) count_kernel<1><<<n_tiles, kEncThreads, 0, st>>>(color, rd, n_cells, tile_len, warp_excl);
-    else count_kernel<3><<<n_tiles, kEncThreads, 0, st>>>(color, rd, n_cells, tile_len, warp_excl);
+    const EncGeom g = bit8 ? make_geom<1>(color, W, n_cells) : make_geom<3>(color, W, n_cells);
+    const uint32_t n_cnt = (n_tiles + kCntTiles - 1) / kCntTiles;
+    if (bit8) count_kernel<1><<<n_cnt, kEncThreads, 0, st>>>(color, g, tile_len, warp_excl);
+    else count_kernel<3><<<n_cnt, kEncThreads, 0, st>>>(color, g, tile_len, warp_excl);
     scan_kernel<<<1, 1024, 0, st>>>(tile_len, n_tiles, tile_off, total);
 #define RTC_LAUNCH_ENC(BPP, GL)                                                                         \
     emit_kernel<BPP, GL><<<n_tiles, kEncThreads, enc_smem(), st>>>(                                     \
-        color, glyph, rd, n_cells, out, (unsigned long long)cap, tile_off, warp_excl)
+        color, glyph, g, out, (unsigned long long)cap, tile_off, warp_excl)
     if (bit8) { if (has_glyph) RTC_LAUNCH_ENC(1, true); else RTC_LAUNCH_ENC(1, false); }
     else      { if (has_glyph) RTC_LAUNCH_ENC(3, true); else RTC_LAUNCH_ENC(3, false); }
 #undef RTC_LAUNCH_ENC
