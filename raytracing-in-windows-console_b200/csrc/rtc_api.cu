@@ -104,7 +104,8 @@ struct rtc_ctx {
     DevBuf<int32_t> d_hit_idx;
     DevBuf<uint8_t> d_color, d_glyph;
     DevBuf<char> d_out;
-    DevBuf<unsigned char> d_desc;           // encoder scratch: per-tile counts + offsets
+    DevBuf<unsigned char> d_desc;           // encoder scratch: per-tile counts, group accumulators (two parities)
+    uint32_t enc_parity = 0;
     DevBuf<unsigned int> d_counters;        // [0..31] trace tile tickets, [32] encode ticket (never reset)
     DevBuf<unsigned long long> d_total;
     DevBuf<float> d_sink;
@@ -174,6 +175,18 @@ rtc::FrameParams make_frame(const rtc_params* p, uint32_t row0, uint32_t row1)
     f.fx = (float)p->x; f.fy = (float)p->y;     // size_t -> float in the reference (RayTracing.cu:16-17)
     f.x = p->x; f.y = p->y; f.row0 = row0; f.row1 = row1;
     return f;
+}
+
+// Encoder scratch: zeroed when (re)allocated; afterwards every launch zeroes the accumulators of the next one.
+int encode_scratch(rtc_ctx* c, uint64_t n_cells)
+{
+    const size_t need = rtc::encode_state_bytes(n_cells);
+    if (need > c->d_desc.cap) {
+        CK(c->d_desc.ensure(need + need / 2));                  // head-room: growing frames do not reallocate every time
+        CK(cudaMemsetAsync(c->d_desc.p, 0, c->d_desc.cap, c->stream));
+    }
+    c->enc_parity ^= 1u;
+    return RTC_OK;
 }
 
 // hoist + trace + shade for rows [row0,row1) into colour/glyph planes (band-relative).
@@ -426,13 +439,14 @@ int rtc_render(rtc_ctx* c, const rtc_params* p, rtc_mode mode, uint32_t flags)
     CK(c->d_color.ensure(n_px * mode_bpp(mode) + 16));
     if (mode_has_glyph(mode)) CK(c->d_glyph.ensure(n_px + 16));
     CK(c->d_out.ensure(cap));
-    CK(c->d_desc.ensure(rtc::encode_state_bytes(n_px)));
+    int rc0 = encode_scratch(c, n_px);
+    if (rc0) return rc0;
     c->have_frame = false;
     int rc = trace_shade(c, p, mode, flags, 0, p->y, c->d_color.p, mode_has_glyph(mode) ? c->d_glyph.p : nullptr, true);
     if (rc) return rc;
     CK(rtc::launch_encode(c->stream, c->d_color.p, mode_has_glyph(mode) ? c->d_glyph.p : nullptr, p->x, p->y, mode,
-                          c->d_out.p, cap, c->d_total.p, c->d_desc.p));
-    c->last_launches += 3;
+                          c->d_out.p, cap, c->d_total.p, c->d_desc.p, c->d_desc.cap, c->enc_parity));
+    c->last_launches += 2;
     CK(cudaEventRecord(c->ev[4], c->stream));
     CK(cudaMemcpyAsync(c->h_total.p, c->d_total.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     c->have_frame = true;
@@ -554,8 +568,10 @@ int rtc_encode(rtc_ctx* c, const uint8_t* dev_color, const uint8_t* dev_glyph, u
     if (mode != RTC_SDL && x > 1 && !dev_color) return fail(RTC_ERR_INVALID, "dev_color is NULL");
     if ((uint64_t)(x - 1u) * y >= (1ull << 31)) return fail(RTC_ERR_CAPACITY, "console size too large");
     CK(cudaSetDevice(c->device));
-    CK(c->d_desc.ensure(rtc::encode_state_bytes((uint64_t)(x - 1u) * y)));
-    CK(rtc::launch_encode(c->stream, dev_color, dev_glyph, x, y, mode, dev_out, cap, dev_total, c->d_desc.p));
+    int rc = encode_scratch(c, (uint64_t)(x - 1u) * y);
+    if (rc) return rc;
+    CK(rtc::launch_encode(c->stream, dev_color, dev_glyph, x, y, mode, dev_out, cap, dev_total, c->d_desc.p, c->d_desc.cap,
+                          c->enc_parity));
     return RTC_OK;
 }
 

@@ -12,14 +12,14 @@
 //         character; one '\n' after each row.  (Proven byte-identical to the reference's scan
 //         by tests)
 //
-// Three launches, no inter-CTA waiting (a fused single-pass version with decoupled look-back -- per slice, per
+// Two launches, no inter-CTA waiting (a fused single-pass version with decoupled look-back -- per slice, per
 // tile, and two-level -- was measured at 0.32-0.44 ms against 0.18 ms: with the store stream saturating HBM the
 // descriptor round trips are exposed; the same kernel with the look-back skipped ran in 0.152 ms.  Kept under
 // scripts/experiments/; numbers in profiles/r01_encode_history.md):
 //   1. count : a tile is 1280 cells = 8 warp slices of 160; writes the tile's emitted byte count and the
 //              exclusive offset of each of its 8 slices (a lane counts 20 consecutive cells here);
-//   2. scan  : one CTA turns the tile counts into exclusive 64-bit offsets + the stream length;
-//   3. emit  : every WARP is autonomous (no CTA barrier after the LUT is staged): it re-derives its
+//              and accumulates group / super-group totals from which any tile's offset is three loads away;
+//   2. emit  : every WARP is autonomous (no CTA barrier after the LUT is staged): it re-derives its
 //              lanes' lengths, prefix-sums them with shuffles, and each lane streams its cells through a
 //              4-byte shift register into a shared-memory image of the warp's slice of the stream.  A full
 //              cell is exactly 5 (3) words, so the byte phase only moves on 1-byte cells; every store is
@@ -32,6 +32,8 @@
 // Algorithmic traffic: BPP (+1) bytes read and the emitted bytes written per cell.
 // (r01a design -- 4 lane-strided cells per thread, byte-granular predicated stores, 3 CTA barriers -- cost
 // 198 thread instructions per cell and was issue-bound at 30 % of HBM peak: profiles/r01a_encode_3pass_ncu.md.)
+#include <algorithm>
+
 #include "rtc_device.cuh"
 #include "rtc_kernels.h"
 
@@ -139,16 +141,20 @@ __device__ __forceinline__ uint32_t full_cells(const uint32_t (&key)[C + 1], uin
 // Counting does not need the emit pass's 5-cells-per-lane layout, only its slice boundaries: here a lane owns
 // kCntC = 20 consecutive cells (8 lanes per 160-cell slice, 4 slices per warp, 4 tiles per CTA), which
 // amortises the address arithmetic over 4x the cells.
+constexpr int kGroupShift = 5, kSuperShift = 10;              // 32 tiles per group, 32 groups per super-group
 constexpr int kCntC = 4 * kEncC;
 constexpr int kCntTiles = kEncThreads * kCntC / kEncTile;      // tiles per count CTA
-static_assert(kCntC * 8 == kEncWarpCells && kCntTiles * kEncTile == kEncThreads * kCntC, "count layout");
+static_assert(kCntC * 8 == kEncWarpCells && kCntTiles * kEncTile == kEncThreads * kCntC && (32 % kCntTiles) == 0, "count layout");
 template <int BPP>
 __global__ void __launch_bounds__(kEncThreads)
-count_kernel(const uint8_t* __restrict__ color, const EncGeom g, uint32_t* __restrict__ tile_len, uint32_t* __restrict__ warp_excl)
+count_kernel(const uint8_t* __restrict__ color, const EncGeom g, uint32_t* __restrict__ tile_len, uint32_t* __restrict__ warp_excl,
+             uint32_t* __restrict__ group_len, uint32_t* __restrict__ super_len, uint32_t* __restrict__ zero_next, uint32_t zero_n)
 {
     constexpr uint32_t CS = BPP == 3 ? 20u : 12u;               // SIZE_RGB / SIZE_8BIT (RayTracing.h:120-123)
     __shared__ uint32_t s_len[kEncThreads / 8];                 // one per slice
     const int tid = threadIdx.x;
+    // the accumulators of the NEXT launch (other parity): nobody reads or writes them during this launch
+    if (blockIdx.x == 0) for (uint32_t i = tid; i < zero_n; i += kEncThreads) zero_next[i] = 0u;
     const uint32_t cell = (blockIdx.x * (uint32_t)kEncThreads + (uint32_t)tid) * kCntC;
     const int n_valid = cell >= g.n_cells ? 0 : (int)min((uint32_t)kCntC, g.n_cells - cell);
     uint32_t len = 0;
@@ -179,59 +185,27 @@ count_kernel(const uint8_t* __restrict__ color, const EncGeom g, uint32_t* __res
             if ((tid & 7) == 0) tile_len[tile] = tot;
         }
     }
-}
-
-// ---- pass 2: exclusive scan of the tile counts (one CTA) ------------------------------------
-// Chunks of 1024 x 32 tiles (one chunk up to 8K frames); a warp owns 1024 consecutive tiles and walks them in 32
-// coalesced rows of 32 (loads issued up front), so tile_len is read and tile_off written in whole lines.
-// A chunk's sum fits 32 bits (32768 tiles x <= 26880 bytes).
-constexpr int kScanRows = 32;
-__global__ void __launch_bounds__(1024)
-scan_kernel(const uint32_t* __restrict__ tile_len, uint32_t n_tiles, unsigned long long* __restrict__ tile_off,
-            unsigned long long* __restrict__ total)
-{
-    __shared__ uint32_t s_warp[32];
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    unsigned long long carry = 0ull;
-    for (uint32_t base = 0; base < n_tiles; base += 1024u * kScanRows) {
-        const uint32_t a = base + warp * (32u * kScanRows) + lane;
-        uint32_t v[kScanRows];
+    if (tid == 0) {                                             // the CTA's 4 tiles share one group and one super-group
+        uint32_t cta = 0;
 #pragma unroll
-        for (int k = 0; k < kScanRows; ++k) v[k] = (a + 32u * k < n_tiles) ? tile_len[a + 32u * k] : 0u;
-        uint32_t run = 0;                                          // exclusive offset inside the warp's tiles
-#pragma unroll
-        for (int k = 0; k < kScanRows; ++k) {
-            uint32_t inc = v[k];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= (uint32_t)o) inc += t;
-            }
-            const uint32_t row_total = __shfl_sync(0xffffffffu, inc, 31);
-            v[k] = run + inc - v[k];
-            run += row_total;
+        for (int w = 0; w < kEncThreads / 8; ++w) cta += s_len[w];
+        const uint32_t tile0 = blockIdx.x * (uint32_t)kCntTiles;
+        if (cta) {
+            atomicAdd(group_len + (tile0 >> kGroupShift), cta);
+            atomicAdd(super_len + (tile0 >> kSuperShift), cta);
         }
-        if (lane == 0u) s_warp[warp] = run;
-        __syncthreads();
-        uint32_t wsum = s_warp[lane];                              // every warp scans the 32 warp sums itself
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, wsum, o);
-            if (lane >= (uint32_t)o) wsum += t;
-        }
-        const uint32_t before = __shfl_sync(0xffffffffu, wsum, (warp + 31u) & 31u);   // inclusive sum of warps < warp
-        const uint32_t chunk_total = __shfl_sync(0xffffffffu, wsum, 31);
-        const unsigned long long wbase = carry + (warp ? before : 0u);
-#pragma unroll
-        for (int k = 0; k < kScanRows; ++k)
-            if (a + 32u * k < n_tiles) tile_off[a + 32u * k] = wbase + v[k];
-        carry += chunk_total;
-        __syncthreads();                                           // s_warp is rewritten by the next chunk
     }
-    if (tid == 0) *total = carry;
 }
 
-// ---- pass 3: emit -----------------------------------------------------------------------------
+// ---- (no scan pass) ---------------------------------------------------------------------------
+// The count pass also accumulates the byte counts of 32-tile groups and of 32-group super-groups (two atomics per
+// count CTA).  An emit warp then obtains its tile's stream offset as
+//     sum(super-groups before mine) + sum(earlier groups of my super-group) + sum(earlier tiles of my group)
+// = three loads per lane + one warp reduction, with no inter-CTA dependency and no third launch.  (A one-CTA scan
+// kernel between the two passes cost 13.5 us however it was written -- row-per-warp shuffles or 32 consecutive
+// tiles per thread -- plus a launch gap: profiles/r01_encode_history.md.)
+
+// ---- pass 2: emit -----------------------------------------------------------------------------
 // One cell into the lane's byte stream.  `acc` holds the last 4 stream bytes, `sel` = 0x7654 - 0x1111*k encodes
 // the k pending (not yet stored) bytes -- the top k bytes of acc -- as the PRMT selector that splices them in
 // front of the next word.
@@ -287,8 +261,9 @@ __device__ __forceinline__ void emit_cells(const uint32_t* __restrict__ s_lut, c
 template <int BPP, bool GLYPH>
 __global__ void __launch_bounds__(kEncThreads)
 emit_kernel(const uint8_t* __restrict__ color, const uint8_t* __restrict__ glyph, const EncGeom g,
-            char* __restrict__ out, unsigned long long cap, const unsigned long long* __restrict__ tile_off,
-            const uint32_t* __restrict__ warp_excl)
+            char* __restrict__ out, unsigned long long cap, const uint32_t* __restrict__ tile_len,
+            const uint32_t* __restrict__ warp_excl, const uint32_t* __restrict__ group_len,
+            const uint32_t* __restrict__ super_len, unsigned long long* __restrict__ total)
 {
     constexpr uint32_t CS = BPP == 3 ? 20u : 12u;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -304,7 +279,17 @@ emit_kernel(const uint8_t* __restrict__ color, const uint8_t* __restrict__ glyph
     const uint32_t t5 = (uint32_t)lane * kEncC;
     const uint32_t cell = cell_w0 + t5;
     const int n_valid = t5 >= n_here ? 0 : (int)min((uint32_t)kEncC, n_here - t5);
-    const unsigned long long goff = tile_off[tile] + warp_excl[(size_t)tile * kEncWarps + warp];
+    // stream offset of this warp's slice (see "no scan pass")
+    unsigned long long goff = warp_excl[(size_t)tile * kEncWarps + warp];
+    {
+        const uint32_t grp = tile >> kGroupShift, sup = tile >> kSuperShift;
+        const uint32_t gi = (sup << (kSuperShift - kGroupShift)) + (uint32_t)lane, ti = (grp << kGroupShift) + (uint32_t)lane;
+        uint32_t v = (gi < grp ? __ldg(group_len + gi) : 0u) + (ti < tile ? __ldg(tile_len + ti) : 0u);
+        if ((uint32_t)lane < sup) v += __ldg(super_len + lane);
+        goff += __reduce_add_sync(0xffffffffu, v);               // < 32 x 2^25 + 2 x 32 x 2^20: fits 32 bits
+        for (uint32_t i = 32u + (uint32_t)lane; i < ((sup + 31u) & ~31u); i += 32u)   // frames beyond 32 super-groups (> 42 Mcells)
+            goff += __reduce_add_sync(0xffffffffu, i < sup ? __ldg(super_len + i) : 0u);
+    }
     unsigned char* stage = smem + 1024 + warp * kEncStageBytes;
 
     // ---- keys, lengths, warp prefix sum --------------------------------------------------------
@@ -335,6 +320,7 @@ emit_kernel(const uint8_t* __restrict__ color, const uint8_t* __restrict__ glyph
         if (lane >= o) inc += t;
     }
     const uint32_t warp_len = __shfl_sync(0xffffffffu, inc, 31);
+    if (lane == 0 && cell_w0 + n_here == g.n_cells) *total = goff + warp_len;   // the frame's last slice
 
     // ---- stream the cells into the staging image (phase-aligned with the output) ---------------
     const uint32_t out_phase = (uint32_t)(reinterpret_cast<uintptr_t>(out + goff) & 15u);
@@ -411,15 +397,22 @@ cudaError_t configure_encode()
     return cudaSuccess;
 }
 
-// scratch: per tile one u64 offset, one u32 count, 8 u32 warp offsets
+// scratch layout (all u32): [parity 0: group_len, super_len][parity 1: same][tile_len][warp_excl x 8].
+// The accumulator capacities follow from the ALLOCATION size, so that the layout (and what "zero everything of the
+// other parity" means) does not change between launches of different frame sizes on the same scratch buffer.
+static uint32_t scratch_tiles(size_t scratch_bytes)              // tiles a scratch allocation can describe
+{
+    return scratch_bytes < 1024 ? 0u : (uint32_t)std::min<size_t>((scratch_bytes - 1024) / (4 + 4 * kEncWarps + 1), 0x7fffffffu);
+}
 size_t encode_state_bytes(uint64_t n_cells)
 {
     const uint64_t n_tiles = (n_cells + kEncTile - 1) / kEncTile + 1;
-    return (size_t)(n_tiles * (8 + 4 + 4 * kEncWarps) + 64);
+    return (size_t)(n_tiles * (4 + 4 * kEncWarps + 1) + 1024 + 64);
 }
 
 cudaError_t launch_encode(cudaStream_t st, const uint8_t* color, const uint8_t* glyph, uint32_t x, uint32_t y,
-                          int mode, char* out, size_t cap, unsigned long long* total, void* scratch)
+                          int mode, char* out, size_t cap, unsigned long long* total, void* scratch, size_t scratch_bytes,
+                          uint32_t parity)
 {
     if (mode == RTC_SDL) {
         newline_kernel<<<(y + 255) / 256, 256, 0, st>>>(out, y, cap, total);
@@ -434,19 +427,25 @@ cudaError_t launch_encode(cudaStream_t st, const uint8_t* color, const uint8_t* 
     if (n_cells64 >= (1ull << 31)) return cudaErrorInvalidValue;
     const uint32_t n_cells = (uint32_t)n_cells64;
     const uint32_t n_tiles = (n_cells + kEncTile - 1) / kEncTile;
-    unsigned long long* tile_off = reinterpret_cast<unsigned long long*>(scratch);
-    uint32_t* tile_len = reinterpret_cast<uint32_t*>(tile_off + n_tiles + 1);
-    uint32_t* warp_excl = tile_len + n_tiles + 1;
+    const uint32_t t_max = scratch_tiles(scratch_bytes);
+    if (n_tiles > t_max) return cudaErrorInvalidValue;
+    const uint32_t n_grp = (t_max >> kGroupShift) + 1u, n_sup = (t_max >> kSuperShift) + 1u;
+    const uint32_t acc_n = (n_grp + n_sup + 3u) & ~3u;           // accumulators per parity
+    uint32_t* base = reinterpret_cast<uint32_t*>(scratch);
+    uint32_t* group_len = base + (parity & 1u) * acc_n;
+    uint32_t* super_len = group_len + n_grp;
+    uint32_t* zero_next = base + ((parity & 1u) ^ 1u) * acc_n;
+    uint32_t* tile_len = base + 2u * acc_n;
+    uint32_t* warp_excl = tile_len + ((t_max + 4u) & ~3u);
     const bool has_glyph = (mode == RTC_BIT_ASCII || mode == RTC_RGB_ASCII) && glyph != nullptr;
     const bool bit8 = (mode == RTC_BIT_ASCII || mode == RTC_BIT_PIXEL);
     const EncGeom g = bit8 ? make_geom<1>(color, W, n_cells) : make_geom<3>(color, W, n_cells);
     const uint32_t n_cnt = (n_tiles + kCntTiles - 1) / kCntTiles;
-    if (bit8) count_kernel<1><<<n_cnt, kEncThreads, 0, st>>>(color, g, tile_len, warp_excl);
-    else count_kernel<3><<<n_cnt, kEncThreads, 0, st>>>(color, g, tile_len, warp_excl);
-    scan_kernel<<<1, 1024, 0, st>>>(tile_len, n_tiles, tile_off, total);
+    if (bit8) count_kernel<1><<<n_cnt, kEncThreads, 0, st>>>(color, g, tile_len, warp_excl, group_len, super_len, zero_next, acc_n);
+    else count_kernel<3><<<n_cnt, kEncThreads, 0, st>>>(color, g, tile_len, warp_excl, group_len, super_len, zero_next, acc_n);
 #define RTC_LAUNCH_ENC(BPP, GL)                                                                         \
     emit_kernel<BPP, GL><<<n_tiles, kEncThreads, enc_smem(), st>>>(                                     \
-        color, glyph, g, out, (unsigned long long)cap, tile_off, warp_excl)
+        color, glyph, g, out, (unsigned long long)cap, tile_len, warp_excl, group_len, super_len, total)
     if (bit8) { if (has_glyph) RTC_LAUNCH_ENC(1, true); else RTC_LAUNCH_ENC(1, false); }
     else      { if (has_glyph) RTC_LAUNCH_ENC(3, true); else RTC_LAUNCH_ENC(3, false); }
 #undef RTC_LAUNCH_ENC

@@ -31,9 +31,11 @@ cudaError_t launch_shade(cudaStream_t st, const FrameParams& fp, int mode, uint3
 // kernel 3 (rtc_encode.cu)
 cudaError_t configure_encode();
 size_t encode_state_bytes(uint64_t n_cells);
-// `scratch`: encode_state_bytes() of device memory (per-tile counts and offsets).  Three launches.
+// `scratch`: >= encode_state_bytes() of device memory, ZEROED when allocated; `parity` must alternate between
+// consecutive launches on the same scratch (each launch zeroes the other parity's accumulators).  Two launches.
 cudaError_t launch_encode(cudaStream_t st, const uint8_t* color, const uint8_t* glyph, uint32_t x, uint32_t y,
-                          int mode, char* out, size_t cap, unsigned long long* total, void* scratch);
+                          int mode, char* out, size_t cap, unsigned long long* total, void* scratch, size_t scratch_bytes,
+                          uint32_t parity);
 
 // physics (rtc_shade.cu)
 cudaError_t launch_update_objects(cudaStream_t st, rtc_object* objs, int n, double dt);
