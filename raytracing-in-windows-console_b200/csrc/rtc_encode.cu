@@ -90,10 +90,34 @@ __device__ __forceinline__ uint32_t row_of(const EncGeom& g, uint32_t n)
 
 // Colour keys of this lane's C consecutive cells (key[1..C]) and of the cell before them (key[0]) from aligned
 // 32-bit loads around an arbitrarily aligned plane.  Words outside the plane are never touched.
-template <int BPP, int C>
+// L2 residency hints: the count pass reads the plane with evict_last, the emit pass writes the stream with
+// evict_first, so that the emit pass finds (most of) a <= 126 MB plane still in L2 instead of re-reading HBM.
+__device__ __forceinline__ unsigned long long l2_policy_evict_last()
+{
+    unsigned long long p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first()
+{
+    unsigned long long p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+template <bool KEEP>
+__device__ __forceinline__ uint32_t ld_plane(const uint32_t* p, unsigned long long policy)
+{
+    uint32_t v;
+    if (KEEP) asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy));
+    else v = __ldg(p);
+    return v;
+}
+
+template <int BPP, int C, bool KEEP>
 __device__ __forceinline__ void load_keys(const uint8_t* __restrict__ color, const EncGeom& g, uint32_t fast_hi, uint32_t cell,
                                           uint32_t (&key)[C + 1])
 {
+    const unsigned long long policy = KEEP ? l2_policy_evict_last() : 0ull;
     constexpr int NIN = EncIn<BPP, C>::NIN;
     const uintptr_t a = reinterpret_cast<uintptr_t>(color) + (size_t)cell * BPP - BPP;   // predecessor key (unused for cell 0)
     const uintptr_t wa = a & ~(uintptr_t)3;
@@ -102,7 +126,7 @@ __device__ __forceinline__ void load_keys(const uint8_t* __restrict__ color, con
     if (cell - 1u < fast_hi) {
         const uint32_t* p = reinterpret_cast<const uint32_t*>(wa);
 #pragma unroll
-        for (int j = 0; j < NIN; ++j) w[j] = __ldg(p + j);
+        for (int j = 0; j < NIN; ++j) w[j] = ld_plane<KEEP>(p + j, policy);
     } else {                                                    // first / last lanes of the frame
 #pragma unroll
         for (int j = 0; j < NIN; ++j) {
@@ -160,7 +184,7 @@ count_kernel(const uint8_t* __restrict__ color, const EncGeom g, uint32_t* __res
     uint32_t len = 0;
     if (n_valid > 0) {
         uint32_t key[kCntC + 1];
-        load_keys<BPP, kCntC>(color, g, g.fast_hi_count, cell, key);
+        load_keys<BPP, kCntC, true>(color, g, g.fast_hi_count, cell, key);
         const uint32_t fm = full_cells<kCntC>(key, cell, n_valid);
         const uint32_t newlines = row_of(g, cell + (uint32_t)n_valid) - row_of(g, cell);   // row ends in [cell, cell + n_valid)
         len = (uint32_t)n_valid + (CS - 1u) * __popc(fm) + newlines;
@@ -295,7 +319,7 @@ emit_kernel(const uint8_t* __restrict__ color, const uint8_t* __restrict__ glyph
     // ---- keys, lengths, warp prefix sum --------------------------------------------------------
     uint32_t key[kEncC + 1], fm = 0, nm = 0, len = 0;
     if (n_valid > 0) {
-        load_keys<BPP, kEncC>(color, g, g.fast_hi_emit, cell, key);
+        load_keys<BPP, kEncC, false>(color, g, g.fast_hi_emit, cell, key);
         fm = full_cells<kEncC>(key, cell, n_valid);
         const uint32_t col = cell - row_of(g, cell) * g.W;
         if (g.W >= (uint32_t)kEncC) {                           // at most one row end among kEncC consecutive cells
@@ -348,8 +372,9 @@ emit_kernel(const uint8_t* __restrict__ color, const uint8_t* __restrict__ glyph
     const uint32_t head = out_phase ? min(16u - out_phase, n_out) : 0u;
     const uint32_t body = (n_out - head) & ~15u;
     if (lane == 0 && body) {
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                     :: "l"(dst + head), "r"((uint32_t)__cvta_generic_to_shared(src + head)), "r"(body) : "memory");
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                     :: "l"(dst + head), "r"((uint32_t)__cvta_generic_to_shared(src + head)), "r"(body), "l"(l2_policy_evict_first())
+                     : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
     if ((uint32_t)lane < head) dst[lane] = (char)src[lane];
