@@ -171,6 +171,15 @@ RTC_API int rtc_frame_hits(rtc_ctx* ctx, const float** host_dist, const int32_t*
  * render, copy the stream to host.                                                        */
 RTC_API int rtc_update(rtc_ctx* ctx, const rtc_params* params, rtc_mode mode, double dt,
                        uint32_t flags, const char** host_ptr, size_t* n_bytes);
+/* The same frame driver, pipelined two deep (the reference's own sink is asynchronous too: Update hands the frame
+ * to a print thread, PrintMachine.cpp:178-192, :257-306).  rtc_submit == rtc_update without the wait: physics step,
+ * render, and the stream length on its way to the host.  rtc_collect returns the OLDEST submitted frame: it waits
+ * for that frame only and copies its stream to pinned host memory on a separate copy stream, so the copy overlaps
+ * the kernels of the frame submitted after it.  At most two frames in flight; the returned buffer stays valid
+ * until the second rtc_submit after this call.
+ *     rtc_submit(f0); for (k = 0; ; ++k) { rtc_submit(f[k+1]); rtc_collect(&ptr, &n); sink(ptr, n); }            */
+RTC_API int rtc_submit(rtc_ctx* ctx, const rtc_params* params, rtc_mode mode, double dt, uint32_t flags);
+RTC_API int rtc_collect(rtc_ctx* ctx, const char** host_ptr, size_t* n_bytes);
 RTC_API int rtc_last_timings(rtc_ctx* ctx, rtc_timings* out);
 
 /* ---- stage-level entry points on caller-owned DEVICE buffers ---------------------------

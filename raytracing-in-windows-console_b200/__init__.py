@@ -22,7 +22,7 @@ EXPORTS = [
     "rtc_create", "rtc_destroy", "rtc_last_error", "rtc_version", "rtc_set_stream", "rtc_device_info",
     "rtc_resize", "rtc_scene_clear", "rtc_scene_add_sphere", "rtc_scene_add_plane", "rtc_scene_set_objects",
     "rtc_scene_get_objects", "rtc_scene_count", "rtc_update_objects", "rtc_render", "rtc_frame_ansi",
-    "rtc_frame_ansi_device", "rtc_frame_color", "rtc_frame_hits", "rtc_update", "rtc_last_timings",
+    "rtc_frame_ansi_device", "rtc_frame_color", "rtc_frame_hits", "rtc_update", "rtc_submit", "rtc_collect", "rtc_last_timings",
     "rtc_trace_band", "rtc_encode", "rtc_encode_capacity", "rtc_mode_bpp", "rtc_mode_has_glyph",
     "rtc_ipc_export", "rtc_ipc_open", "rtc_ipc_close", "rtc_camera_params", "rtc_fp32_peak",
 ]
@@ -73,6 +73,8 @@ def load_library(build_if_missing=True):
     L.rtc_frame_color.argtypes = [vp, c.POINTER(vp), c.POINTER(u32), c.POINTER(vp)]
     L.rtc_frame_hits.argtypes = [vp, c.POINTER(vp), c.POINTER(vp)]
     L.rtc_update.argtypes = [vp, vp, i32, f64, u32, c.POINTER(vp), c.POINTER(sz)]
+    L.rtc_submit.argtypes = [vp, vp, i32, f64, u32]
+    L.rtc_collect.argtypes = [vp, c.POINTER(vp), c.POINTER(sz)]
     L.rtc_last_timings.argtypes = [vp, vp]
     L.rtc_trace_band.argtypes = [vp, vp, i32, u32, u32, u32, vp, vp]
     L.rtc_encode.argtypes = [vp, vp, vp, u32, u32, i32, vp, sz, vp]
@@ -206,6 +208,17 @@ class Context:
         p, n = ctypes.c_void_p(), ctypes.c_size_t()
         _check(self.L.rtc_update(self._h, ctypes.byref(params), mode, float(dt), flags, ctypes.byref(p), ctypes.byref(n)))
         return _view(p.value, n.value, np.uint8)
+
+    def submit(self, params, mode, dt=0.0, flags=0):
+        """Pipelined Update, part 1: enqueue physics + render (returns at once; at most two frames in flight)."""
+        _check(self.L.rtc_submit(self._h, ctypes.byref(params), mode, float(dt), flags))
+
+    def collect(self, copy=False):
+        """Pipelined Update, part 2: the oldest submitted frame's stream, in pinned host memory."""
+        p, n = ctypes.c_void_p(), ctypes.c_size_t()
+        _check(self.L.rtc_collect(self._h, ctypes.byref(p), ctypes.byref(n)))
+        v = _view(p.value, n.value, np.uint8)
+        return v.copy() if copy else v
 
     def timings(self):
         t = RtcTimings()

@@ -94,8 +94,10 @@ struct rtc_ctx {
     std::vector<int32_t> sphere_obj, plane_obj;
     bool scene_dirty = true;       // host -> device upload pending
     bool host_stale = false;       // device physics ran; host copy must be refreshed before use
-    DevBuf<rtc_object> d_objs;
-    DevBuf<int32_t> d_sphere_obj, d_plane_obj;
+    // device scene: ONE blob [objects | sphere index list | plane index list] so that an upload is a single copy
+    DevBuf<unsigned char> d_scene;
+    struct View { rtc_object* p = nullptr; } d_objs;
+    struct ViewI { int32_t* p = nullptr; } d_sphere_obj, d_plane_obj;
     DevBuf<float> d_fast;      // 12 B per sphere slot (slots padded to a multiple of 4)
     DevBuf<float4> d_exact;
 
@@ -103,14 +105,21 @@ struct rtc_ctx {
     DevBuf<float> d_hit_t;
     DevBuf<int32_t> d_hit_idx;
     DevBuf<uint8_t> d_color, d_glyph;
-    DevBuf<char> d_out;
+    DevBuf<char> d_out[2];                  // two frame slots: the stream of frame k is copied out while k+1 is encoded
     DevBuf<unsigned char> d_desc;           // encoder scratch: per-tile counts, group accumulators (two parities)
     uint32_t enc_parity = 0;
     DevBuf<unsigned int> d_counters;        // [0..31] trace tile tickets, [32] encode ticket (never reset)
-    DevBuf<unsigned long long> d_total;
+    DevBuf<unsigned long long> d_total;     // [2]
     DevBuf<float> d_sink;
-    PinBuf<unsigned long long> h_total;
-    PinBuf<char> h_out;
+    PinBuf<unsigned long long> h_total;     // [2]
+    PinBuf<char> h_out[2];
+    PinBuf<unsigned char> h_scene[2];       // pinned staging of the scene upload (objects + index lists)
+    int scene_slot = 0;
+    cudaStream_t copy_stream = nullptr;     // D2H of finished streams, concurrent with the next frame's kernels
+    cudaEvent_t ev_total[2] = {nullptr, nullptr};   // slot's encode finished and its length is on the host
+    int cur = 0;                            // slot of the last rtc_render
+    int fifo[2] = {0, 0}, fifo_n = 0;       // submitted, not yet collected slots (oldest first)
+    size_t slot_cap[2] = {0, 0};
     PinBuf<uint8_t> h_color, h_glyph;
     PinBuf<float> h_hit_t;
     PinBuf<int32_t> h_hit_idx;
@@ -119,7 +128,6 @@ struct rtc_ctx {
     bool have_frame = false;
     int last_mode = RTC_RGB_PIXEL;
     uint32_t last_x = 0, last_y = 0;
-    size_t last_cap = 0;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool timings_valid = false;
     uint32_t last_launches = 0;
@@ -138,19 +146,30 @@ int upload_scene(rtc_ctx* c)
         else if (c->objs[i].type == RTC_OBJ_PLANE) c->plane_obj.push_back((int32_t)i);
     }
     const size_t n_slots = (c->sphere_obj.size() + 3) & ~(size_t)3;
-    CK(c->d_objs.ensure(n > 0 ? n : 1));
-    CK(c->d_sphere_obj.ensure(n_slots > 0 ? n_slots : 4));
-    CK(c->d_plane_obj.ensure(c->plane_obj.size() > 0 ? c->plane_obj.size() : 1));
     CK(c->d_fast.ensure(n_slots > 0 ? 3 * n_slots : 12));
     CK(c->d_exact.ensure(n_slots > 0 ? n_slots : 4));
-    // Pageable sources: cudaMemcpyAsync stages them before returning, so the vectors may change afterwards.
-    if (n) CK(cudaMemcpyAsync(c->d_objs.p, c->objs.data(), n * sizeof(rtc_object), cudaMemcpyHostToDevice, c->stream));
-    if (!c->sphere_obj.empty())
-        CK(cudaMemcpyAsync(c->d_sphere_obj.p, c->sphere_obj.data(), c->sphere_obj.size() * sizeof(int32_t),
-                           cudaMemcpyHostToDevice, c->stream));
-    if (!c->plane_obj.empty())
-        CK(cudaMemcpyAsync(c->d_plane_obj.p, c->plane_obj.data(), c->plane_obj.size() * sizeof(int32_t),
-                           cudaMemcpyHostToDevice, c->stream));
+    // Stage in pinned memory (two slots: the previous upload may still be in flight), then ONE async copy.
+    const size_t b_objs = (n * sizeof(rtc_object) + 63) & ~(size_t)63, b_sph = (n_slots * sizeof(int32_t) + 63) & ~(size_t)63,
+                 b_pl = (c->plane_obj.size() * sizeof(int32_t) + 63) & ~(size_t)63;
+    const size_t b_all = b_objs + b_sph + b_pl + 64;
+    if (b_all > c->d_scene.cap) {
+        CK(cudaStreamSynchronize(c->stream));                   // (the host copy is authoritative here: nothing to keep)
+        CK(c->d_scene.ensure(b_all * 2));
+    }
+    c->d_objs.p = reinterpret_cast<rtc_object*>(c->d_scene.p);
+    c->d_sphere_obj.p = reinterpret_cast<int32_t*>(c->d_scene.p + b_objs);
+    c->d_plane_obj.p = reinterpret_cast<int32_t*>(c->d_scene.p + b_objs + b_sph);
+    c->scene_slot ^= 1;
+    PinBuf<unsigned char>& st = c->h_scene[c->scene_slot];
+    if (b_all > st.cap) {
+        CK(cudaStreamSynchronize(c->stream));
+        CK(st.ensure(b_all * 2));
+    }
+    unsigned char* h = st.p;
+    if (n) memcpy(h, c->objs.data(), n * sizeof(rtc_object));
+    if (!c->sphere_obj.empty()) memcpy(h + b_objs, c->sphere_obj.data(), c->sphere_obj.size() * sizeof(int32_t));
+    if (!c->plane_obj.empty()) memcpy(h + b_objs + b_sph, c->plane_obj.data(), c->plane_obj.size() * sizeof(int32_t));
+    CK(cudaMemcpyAsync(c->d_scene.p, h, b_all - 64, cudaMemcpyHostToDevice, c->stream));
     c->scene_dirty = false;
     return RTC_OK;
 }
@@ -291,9 +310,11 @@ int rtc_create(rtc_ctx** out, int device)
     CKC(rtc::configure_encode());
     CKC(c->d_counters.ensure(rtc::kNumCounters));
     CKC(cudaMemset(c->d_counters.p, 0, rtc::kNumCounters * sizeof(unsigned int)));
-    CKC(c->d_total.ensure(1));
+    CKC(c->d_total.ensure(2));
+    CKC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (auto& ev : c->ev_total) CKC(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CKC(c->d_sink.ensure(4));
-    CKC(c->h_total.ensure(1));
+    CKC(c->h_total.ensure(2));
 #undef CKC
     *out = c;
     return RTC_OK;
@@ -304,10 +325,13 @@ void rtc_destroy(rtc_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
-    c->d_objs.release(); c->d_sphere_obj.release(); c->d_plane_obj.release(); c->d_fast.release(); c->d_exact.release();
-    c->d_hit_t.release(); c->d_hit_idx.release(); c->d_color.release(); c->d_glyph.release(); c->d_out.release();
+    c->d_scene.release(); c->d_fast.release(); c->d_exact.release();
+    c->d_hit_t.release(); c->d_hit_idx.release(); c->d_color.release(); c->d_glyph.release(); c->d_out[0].release(); c->d_out[1].release();
     c->d_desc.release(); c->d_counters.release(); c->d_total.release(); c->d_sink.release();
-    c->h_total.release(); c->h_out.release(); c->h_color.release(); c->h_glyph.release();
+    c->h_total.release(); c->h_out[0].release(); c->h_out[1].release(); c->h_scene[0].release(); c->h_scene[1].release();
+    c->h_color.release(); c->h_glyph.release();
+    for (auto& ev : c->ev_total) if (ev) cudaEventDestroy(ev);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     c->h_hit_t.release(); c->h_hit_idx.release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -438,20 +462,24 @@ int rtc_render(rtc_ctx* c, const rtc_params* p, rtc_mode mode, uint32_t flags)
     const size_t cap = rtc_encode_capacity(p->x, p->y, mode);
     CK(c->d_color.ensure(n_px * mode_bpp(mode) + 16));
     if (mode_has_glyph(mode)) CK(c->d_glyph.ensure(n_px + 16));
-    CK(c->d_out.ensure(cap));
+    const int slot = c->cur ^ 1;                               // the other slot may still be draining to the host
+    CK(c->d_out[slot].ensure(cap));
     int rc0 = encode_scratch(c, n_px);
     if (rc0) return rc0;
     c->have_frame = false;
     int rc = trace_shade(c, p, mode, flags, 0, p->y, c->d_color.p, mode_has_glyph(mode) ? c->d_glyph.p : nullptr, true);
     if (rc) return rc;
     CK(rtc::launch_encode(c->stream, c->d_color.p, mode_has_glyph(mode) ? c->d_glyph.p : nullptr, p->x, p->y, mode,
-                          c->d_out.p, cap, c->d_total.p, c->d_desc.p, c->d_desc.cap, c->enc_parity));
+                          c->d_out[slot].p, cap, c->d_total.p + slot, c->d_desc.p, c->d_desc.cap, c->enc_parity));
     c->last_launches += 2;
     CK(cudaEventRecord(c->ev[4], c->stream));
-    CK(cudaMemcpyAsync(c->h_total.p, c->d_total.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_total.p + slot, c->d_total.p + slot, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaEventRecord(c->ev_total[slot], c->stream));
+    c->cur = slot;
+    c->slot_cap[slot] = cap;
     c->have_frame = true;
     c->timings_valid = true;
-    c->last_mode = mode; c->last_x = p->x; c->last_y = p->y; c->last_cap = cap;
+    c->last_mode = mode; c->last_x = p->x; c->last_y = p->y;
     return RTC_OK;
 }
 
@@ -461,9 +489,9 @@ int rtc_frame_ansi_device(rtc_ctx* c, const char** dev_ptr, size_t* n_bytes)
     if (!c->have_frame) return fail(RTC_ERR_INVALID, "no frame rendered");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
-    const size_t n = (size_t)c->h_total.p[0];
-    if (n > c->last_cap) return fail(RTC_ERR_CAPACITY, "stream (%zu B) exceeds capacity (%zu B)", n, c->last_cap);
-    *dev_ptr = c->d_out.p; *n_bytes = n;
+    const size_t n = (size_t)c->h_total.p[c->cur];
+    if (n > c->slot_cap[c->cur]) return fail(RTC_ERR_CAPACITY, "stream (%zu B) exceeds capacity (%zu B)", n, c->slot_cap[c->cur]);
+    *dev_ptr = c->d_out[c->cur].p; *n_bytes = n;
     return RTC_OK;
 }
 
@@ -473,10 +501,43 @@ int rtc_frame_ansi(rtc_ctx* c, const char** host_ptr, size_t* n_bytes)
     size_t n = 0;
     int rc = rtc_frame_ansi_device(c, &dptr, &n);
     if (rc) return rc;
-    CK(c->h_out.ensure(n > 0 ? n : 1));
-    if (n) CK(cudaMemcpyAsync(c->h_out.p, dptr, n, cudaMemcpyDeviceToHost, c->stream));
+    PinBuf<char>& h = c->h_out[c->cur];
+    if (n > h.cap) CK(h.ensure(n + n / 2 + 4096));
+    if (n) CK(cudaMemcpyAsync(h.p, dptr, n, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    *host_ptr = c->h_out.p; *n_bytes = n;
+    *host_ptr = h.p; *n_bytes = n;
+    return RTC_OK;
+}
+
+// ---- pipelined frames: submit frame k+1, then collect frame k ------------------------------------------------
+int rtc_submit(rtc_ctx* c, const rtc_params* p, rtc_mode mode, double dt, uint32_t flags)
+{
+    if (!c) return fail(RTC_ERR_INVALID, "ctx is NULL");
+    if (c->fifo_n >= 2) return fail(RTC_ERR_INVALID, "two frames are already in flight: rtc_collect one first");
+    int rc = rtc_update_objects(c, dt, flags);
+    if (rc) return rc;
+    rc = rtc_render(c, p, mode, flags);
+    if (rc) return rc;
+    c->fifo[c->fifo_n++] = c->cur;
+    return RTC_OK;
+}
+
+int rtc_collect(rtc_ctx* c, const char** host_ptr, size_t* n_bytes)
+{
+    if (!c || !host_ptr || !n_bytes) return fail(RTC_ERR_INVALID, "NULL argument");
+    if (c->fifo_n == 0) return fail(RTC_ERR_INVALID, "no frame in flight");
+    CK(cudaSetDevice(c->device));
+    const int slot = c->fifo[0];
+    c->fifo[0] = c->fifo[1];
+    --c->fifo_n;
+    CK(cudaEventSynchronize(c->ev_total[slot]));               // this frame's kernels are done; the next frame's keep running
+    const size_t n = (size_t)c->h_total.p[slot];
+    if (n > c->slot_cap[slot]) return fail(RTC_ERR_CAPACITY, "stream (%zu B) exceeds capacity (%zu B)", n, c->slot_cap[slot]);
+    PinBuf<char>& h = c->h_out[slot];
+    if (n > h.cap) CK(h.ensure(n + n / 2 + 4096));
+    if (n) CK(cudaMemcpyAsync(h.p, c->d_out[slot].p, n, cudaMemcpyDeviceToHost, c->copy_stream));
+    CK(cudaStreamSynchronize(c->copy_stream));
+    *host_ptr = h.p; *n_bytes = n;
     return RTC_OK;
 }
 

@@ -294,3 +294,29 @@ def test_many_spheres_chunked(ctx, oracle, rtc):
     objs = scenes.random_spheres(9000, 31)
     p = rtc.camera_params(49, 20, (0, 0, -120), (0, PI32, 0), 1.0 / 48)
     check_frame(ctx, oracle, objs, p, RGB_PIXEL)
+
+
+def test_pipelined_submit_collect(ctx, rtc):
+    """rtc_submit / rtc_collect (two frames in flight, stream copied out on the copy stream while the next
+    frame renders) == the synchronous rtc_update, frame by frame, with physics and a moving camera."""
+    objs = scenes.random_spheres(200, 5)
+    ps = [rtc.camera_params(321, 100, (0.7 * k, 0, -120), (0, PI32, 0), 1.0 / 320) for k in range(6)]
+    modes = [RGB_PIXEL, RGB_ASCII, BIT_PIXEL, RGB_PIXEL, BIT_ASCII, RGB_PIXEL]
+    ctx.set_objects(objs)
+    want = [np.array(ctx.update(p, m, dt=0.11)) for p, m in zip(ps, modes)]
+    ctx.set_objects(objs)
+    got = []
+    ctx.submit(ps[0], modes[0], dt=0.11)
+    for k in range(len(ps)):
+        if k + 1 < len(ps):
+            ctx.submit(ps[k + 1], modes[k + 1], dt=0.11)
+        got.append(ctx.collect(copy=True))
+    for k in range(len(ps)):
+        assert np.array_equal(got[k], want[k]), f"frame {k}"
+    with pytest.raises(rtc.RtcError, match="no frame in flight"):
+        ctx.collect()
+    ctx.submit(ps[0], RGB_PIXEL)
+    ctx.submit(ps[1], RGB_PIXEL)
+    with pytest.raises(rtc.RtcError, match="in flight"):
+        ctx.submit(ps[2], RGB_PIXEL)
+    ctx.collect(); ctx.collect()
