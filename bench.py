@@ -37,7 +37,8 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config3_4k_1024")
     ap.add_argument("--mode", default="RGB_PIXEL")
-    ap.add_argument("--gather", default="nccl", choices=["nccl", "ipc"])
+    ap.add_argument("--gather", default="ipc", choices=["nccl", "ipc"])
+    ap.add_argument("--orbit", type=int, default=0, help="camera orbit of this many frames (config 4: 120); 0 = fixed camera")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
@@ -228,7 +229,6 @@ def run_ours(args):
     import torch
     import rtc_b200
     from rtc_b200 import multigpu, scenes
-    band = multigpu.band
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -246,6 +246,14 @@ def run_ours(args):
     name = args.workload
     objs = scenes.config_scene(name)
     p = scenes.config_camera(name)
+    # --orbit N: frame i is seen from camera i mod N of an N-frame orbit about the scene centre
+    cams = [scenes.config_camera(name, frame=k, n_frames=args.orbit) for k in range(args.orbit)] if args.orbit > 0 else [p]
+    frame_no = [0]
+
+    def next_cam():
+        c = cams[frame_no[0] % len(cams)]
+        frame_no[0] += 1
+        return c
     x, y = p.x, p.y
     W = x - 1
     bpp = rtc_b200.mode_bpp(mode)
@@ -260,48 +268,30 @@ def run_ours(args):
     ctx.set_objects(objs)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")      # > 126 MB L2
 
-    r0, r1 = band(y, rank, world)
     cap = rtc_b200.encode_capacity(x, y, mode)
     launches_per_step = 0
+    renderer = None
+    deficit = 0.0
     if world == 1:
         def step():
-            ctx.render(p, mode)
+            ctx.render(next_cam(), mode)
     else:
-        # row bands: every rank traces + shades its band; bands are gathered into rank 0's frame
-        # buffer (NCCL send/recv, or written straight into it over NVLink through a CUDA-IPC mapping);
-        # rank 0 encodes the assembled frame.
-        frame_color = torch.empty(W * y * bpp + 16, dtype=torch.uint8, device="cuda") if rank == 0 else None
-        frame_glyph = torch.empty(W * y + 16, dtype=torch.uint8, device="cuda") if (rank == 0 and has_glyph) else None
-        band_color = torch.empty(max(1, (r1 - r0) * W * bpp), dtype=torch.uint8, device="cuda")
-        band_glyph = torch.empty(max(1, (r1 - r0) * W), dtype=torch.uint8, device="cuda") if has_glyph else None
-        out = torch.empty(cap, dtype=torch.uint8, device="cuda") if rank == 0 else None
-        total = torch.zeros(1, dtype=torch.int64, device="cuda") if rank == 0 else None
-        bands = [band(y, g, world) for g in range(world)]
-        peer_color = peer_glyph = 0
-        if args.gather == "ipc":
-            handles = [None, None]
-            if rank == 0:
-                handles = [ctx.ipc_export(frame_color.data_ptr()), ctx.ipc_export(frame_glyph.data_ptr()) if has_glyph else None]
-            dist.broadcast_object_list(handles, src=0)
-            if rank != 0:
-                peer_color = ctx.ipc_open(handles[0])
-                peer_glyph = ctx.ipc_open(handles[1]) if has_glyph else 0
-            else:
-                peer_color = frame_color.data_ptr()
-                peer_glyph = frame_glyph.data_ptr() if has_glyph else 0
+        # Row bands: every rank traces + shades its band straight into (ipc) or followed by NCCL send/recv into (nccl)
+        # rank 0's frame planes; rank 0 encodes the assembled frame.  Rank 0 also pays for the encoder, so it gets a
+        # smaller band: the deficit (in rows) is measured on rank 0 from one whole frame's stage timings.
+        hdr = [0.0]
+        if rank == 0:
+            for _ in range(3):
+                ctx.render(p, mode)
+            torch.cuda.synchronize()
+            t = ctx.timings()
+            hdr = [t["encode_ms"] / max(1e-9, (t["trace_ms"] + t["shade_ms"]) / y)]
+        dist.broadcast_object_list(hdr, src=0)
+        deficit = float(hdr[0])
+        renderer = multigpu.BandRenderer(ctx, dist, rank, world, x, y, mode, gather=args.gather, deficit_rows=deficit)
 
         def step():
-            if args.gather == "ipc":
-                ctx.trace_band(p, mode, r0, r1, peer_color + r0 * W * bpp, (peer_glyph + r0 * W) if has_glyph else 0)
-                dist.barrier()                     # stream-ordered: all bands have landed in GPU 0's HBM
-            else:
-                dst_c = frame_color[r0 * W * bpp:r1 * W * bpp] if rank == 0 else band_color
-                dst_g = (frame_glyph[r0 * W:r1 * W] if rank == 0 else band_glyph) if has_glyph else None
-                ctx.trace_band(p, mode, r0, r1, dst_c.data_ptr(), dst_g.data_ptr() if has_glyph else 0)
-                multigpu.gather_planes(dist, rank, world, y, W, bpp, band_color, frame_color, band_glyph, frame_glyph)
-            if rank == 0:
-                ctx.encode(frame_color.data_ptr(), frame_glyph.data_ptr() if has_glyph else 0, x, y, mode,
-                           out.data_ptr(), cap, total.data_ptr())
+            return renderer.step(next_cam())
 
     def sync_all():
         torch.cuda.synchronize()
@@ -359,7 +349,7 @@ def run_ours(args):
         nbytes = 0
         for _ in range(args.steps):
             ctx.set_objects(objs)                  # scene + camera block from host memory every frame
-            ctx.submit(p, mode, 0.0, upd_flags)    # frame k+1
+            ctx.submit(next_cam(), mode, 0.0, upd_flags)    # frame k+1
             s = ctx.collect()                      # frame k: stream in pinned host memory
             nbytes = len(s)
         t1 = time.perf_counter()
@@ -379,26 +369,48 @@ def run_ours(args):
                "device_ms_of_last_pipelined_frame": dev_ms_in_pipeline,
                "synchronous_rtc_update": {"value": frame_rays / (sync_ms * 1e-3) / 1e6, "ms_per_step": sync_ms}}
     else:
-        host = torch.empty(cap, dtype=torch.uint8, pin_memory=True) if rank == 0 else None
+        # Pipelined like rtc_submit / rtc_collect: frame k+1 is enqueued on every rank before rank 0 waits for frame k's
+        # stream length and copies the stream to pinned host memory on a separate copy stream.
+        host = [torch.empty(cap, dtype=torch.uint8, pin_memory=True) for _ in range(2)] if rank == 0 else None
+        copy_stream = torch.cuda.Stream()
+        done = [torch.cuda.Event(), torch.cuda.Event()]
+        h_total = torch.zeros(2, dtype=torch.int64, pin_memory=True) if rank == 0 else None
+
+        def submit():
+            ctx.set_objects(objs)
+            sl = renderer.step(next_cam())
+            if rank == 0:
+                h_total[sl:sl + 1].copy_(renderer.total[sl:sl + 1], non_blocking=True)
+                done[sl].record(stream)
+            return sl
+
+        def collect(sl):
+            if rank != 0:
+                return 0
+            done[sl].synchronize()
+            n = int(h_total[sl])
+            with torch.cuda.stream(copy_stream):
+                host[sl][:n].copy_(renderer.out[sl][:n], non_blocking=True)
+            copy_stream.synchronize()
+            return n
+
         sync_all()
+        prev = submit()
         t0 = time.perf_counter()
         nbytes = 0
         for _ in range(args.steps):
-            ctx.set_objects(objs)
-            step()
-            if rank == 0:
-                n = int(total.item())              # D2H of the length (syncs the stream)
-                host[:n].copy_(out[:n], non_blocking=True)
-                torch.cuda.synchronize()
-                nbytes = n
-        sync_all()
+            cur = submit()
+            nbytes = collect(prev)
+            prev = cur
         t1 = time.perf_counter()
+        collect(prev)
+        sync_all()
         tt = torch.tensor([(t1 - t0) * 1e3 / args.steps], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_ms = float(tt.item())
         e2e = {"value": frame_rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": int(objs.nbytes + 96) * world, "d2h_bytes_per_step": int(nbytes + 8),
-               "api": "rtc_scene_set_objects + rtc_trace_band per rank, gather to GPU 0, rtc_encode, stream copied to pinned host memory"}
+               "api": "per rank rtc_scene_set_objects + rtc_trace_band, bands gathered to GPU 0, rtc_encode, stream copied to pinned host memory (pipelined two deep)"}
 
     if rank != 0:
         if dist is not None:
@@ -414,7 +426,9 @@ def run_ours(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": name, "x": x, "y": y, "rays_per_frame": frame_rays, "spheres": n_spheres,
                    "objects": int(len(objs)), "mode": args.mode, "parallelism": "rowband%d" % world,
-                   "gather": args.gather if world > 1 else None, "l2": "flushed between timed steps (256 MiB memset, untimed)"},
+                   "gather": args.gather if world > 1 else None,
+                   "bands": renderer.bands if renderer is not None else [[0, y]], "camera_orbit_frames": args.orbit,
+                   "l2": "flushed between timed steps (256 MiB memset, untimed)"},
         "frames_per_s": 1e3 / ms_per_step,
         "clocks": clocks, "e2e": e2e,
     }

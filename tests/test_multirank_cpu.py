@@ -68,3 +68,19 @@ def test_band_partition_properties(rtc):
             assert all(bs[i][1] == bs[i + 1][0] for i in range(world - 1))          # contiguous, no overlap
             sizes = [b - a for a, b in bs]
             assert max(sizes) - min(sizes) <= 1                                      # balanced to one row
+
+
+def test_weighted_bands(rtc):
+    """Rank 0 also encodes, so it gets fewer rows; the cover stays exact and contiguous."""
+    from rtc_b200 import multigpu
+    for y in (1, 7, 64, 2160, 4321):
+        for world in (1, 2, 3, 8):
+            assert multigpu.weighted_bands(y, world, 0.0) == multigpu.bands(y, world)
+            for d in (0.5, 3.7, 62.0, 1e9):
+                bs = multigpu.weighted_bands(y, world, d)
+                assert len(bs) == world and bs[0][0] == 0 and bs[-1][1] == y
+                assert all(bs[i][1] == bs[i + 1][0] and bs[i][0] <= bs[i][1] for i in range(world - 1))
+                if world > 1:
+                    others = [b - a for a, b in bs[1:]]
+                    assert bs[0][1] - bs[0][0] <= max(others) and max(others) - min(others) <= 1
+    assert multigpu.weighted_bands(2160, 8, 62.0)[0] == (0, 216)
