@@ -39,6 +39,7 @@ def parse_args():
     ap.add_argument("--mode", default="RGB_PIXEL")
     ap.add_argument("--gather", default="ipc", choices=["nccl", "ipc"])
     ap.add_argument("--orbit", type=int, default=0, help="camera orbit of this many frames (config 4: 120); 0 = fixed camera")
+    ap.add_argument("--shadows", action="store_true", help="shadow-ray extension on (second, light-origin trace pass)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
@@ -249,6 +250,7 @@ def run_ours(args):
     # --orbit N: frame i is seen from camera i mod N of an N-frame orbit about the scene centre
     cams = [scenes.config_camera(name, frame=k, n_frames=args.orbit) for k in range(args.orbit)] if args.orbit > 0 else [p]
     frame_no = [0]
+    rflags = rtc_b200.FLAG_SHADOWS if args.shadows else 0
 
     def next_cam():
         c = cams[frame_no[0] % len(cams)]
@@ -274,7 +276,7 @@ def run_ours(args):
     deficit = 0.0
     if world == 1:
         def step():
-            ctx.render(next_cam(), mode)
+            ctx.render(next_cam(), mode, rflags)
     else:
         # Row bands: every rank traces + shades its band straight into (ipc) or followed by NCCL send/recv into (nccl)
         # rank 0's frame planes; rank 0 encodes the assembled frame.  Rank 0 also pays for the encoder, so it gets a
@@ -291,7 +293,7 @@ def run_ours(args):
         renderer = multigpu.BandRenderer(ctx, dist, rank, world, x, y, mode, gather=args.gather, deficit_rows=deficit)
 
         def step():
-            return renderer.step(next_cam())
+            return renderer.step(next_cam(), rflags)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -338,7 +340,7 @@ def run_ours(args):
         # Pipelined public API (rtc_submit / rtc_collect, the asynchronous form of RayTracingManager::Update): every
         # step uploads the scene + camera block from (pinned-staged) host memory and brings that step's stream back
         # to pinned host memory; the D2H of frame k overlaps the kernels of frame k+1.
-        upd_flags = rtc_b200.FLAG_UPDATE_REF_LAUNCH_LIMIT
+        upd_flags = rtc_b200.FLAG_UPDATE_REF_LAUNCH_LIMIT | rflags
         for _ in range(2):
             ctx.set_objects(objs)
             s = ctx.update(p, mode, dt=0.0, flags=upd_flags)
@@ -378,7 +380,7 @@ def run_ours(args):
 
         def submit():
             ctx.set_objects(objs)
-            sl = renderer.step(next_cam())
+            sl = renderer.step(next_cam(), rflags)
             if rank == 0:
                 h_total[sl:sl + 1].copy_(renderer.total[sl:sl + 1], non_blocking=True)
                 done[sl].record(stream)
@@ -427,7 +429,7 @@ def run_ours(args):
         "config": {"workload": name, "x": x, "y": y, "rays_per_frame": frame_rays, "spheres": n_spheres,
                    "objects": int(len(objs)), "mode": args.mode, "parallelism": "rowband%d" % world,
                    "gather": args.gather if world > 1 else None,
-                   "bands": renderer.bands if renderer is not None else [[0, y]], "camera_orbit_frames": args.orbit,
+                   "bands": renderer.bands if renderer is not None else [[0, y]], "camera_orbit_frames": args.orbit, "shadow_rays": bool(args.shadows),
                    "l2": "flushed between timed steps (256 MiB memset, untimed)"},
         "frames_per_s": 1e3 / ms_per_step,
         "clocks": clocks, "e2e": e2e,
@@ -435,7 +437,8 @@ def run_ours(args):
     if world == 1:
         trace_ms = stage["trace_ms"] / args.steps
         enc_ms = stage["encode_ms"] / args.steps
-        achieved = 7.0 * frame_rays * n_spheres / (trace_ms * 1e-3) / 1e12
+        n_passes = 2 if args.shadows else 1                    # the shadow pass runs the same packed test over every tile with a shaded pixel
+        achieved = 7.0 * frame_rays * n_spheres * n_passes / (trace_ms * 1e-3) / 1e12
         try:
             measured_ffma = max(ctx.fp32_peak(0, 3000)[0] for _ in range(2))
             measured_ffma2 = max(ctx.fp32_peak(1, 3000)[0] for _ in range(2))
@@ -446,7 +449,7 @@ def run_ours(args):
                             "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": None,
                             "peak_source": "%d SMs x 128 lanes x 2 FLOP x %.0f MHz (%s sm_max_mhz); not in MEASURED_PEAKS.json, which has HBM and bf16 tensor only"
                                            % (sm_count, pk["sm_max_mhz"], pk["source"]),
-                            "algorithmic_flops_per_launch": 7.0 * frame_rays * n_spheres, "kernel_ms": trace_ms,
+                            "algorithmic_flops_per_launch": 7.0 * frame_rays * n_spheres, "launches_in_kernel_ms": n_passes, "kernel_ms": trace_ms,
                             "measured_ffma_tflops": measured_ffma, "measured_ffma2_tflops": measured_ffma2,
                             "frac_of_measured_ffma": (achieved / measured_ffma) if measured_ffma else None}
         enc_bytes = bpp * frame_rays + n_stream

@@ -68,9 +68,10 @@ enum { RTC_OBJ_NONE = 0, RTC_OBJ_PLANE = 1, RTC_OBJ_SPHERE = 2 };
 /* Flags for rtc_render / rtc_trace_band / rtc_update_objects. */
 enum {
     RTC_FLAG_NONE = 0u,
-    /* Extension (NOT in the reference, which casts no shadow rays -- SURVEY F1): any-hit
-     * query from the shaded point toward the light (1,50,0); occluded pixels keep only the
-     * ambient term.  Off by default; all parity claims are made with it off.            */
+    /* Extension (NOT in the reference, which casts no shadow rays -- SURVEY F1): one shadow ray
+     * per shaded pixel, cast from the light (1,50,0) toward the shaded point lifted 1e-3 along
+     * its normal; a point with an object strictly nearer to the light keeps only the ambient
+     * term.  Off by default; all parity claims are made with it off.                      */
     RTC_FLAG_SHADOWS = 1u << 0,
     /* rtc_update_objects: mirror the reference's launch bug -- its UpdateObjects launch
      * uses block = count threads, which CUDA rejects when count > 1024, so no object moves

@@ -150,22 +150,23 @@ typedef struct {
     int32_t lit;         /* shadow extension: 1 unless the shadow ray was blocked            */
 } hit_rec;
 
-/* Extension (not in the reference): any-hit occlusion toward the light, built from the
- * reference's own Trace functions.  Origin = P + n*1e-3, in shadow iff some
- * object is hit at 0 <= t < |L - P'|.                                                      */
+/* Shadow-ray EXTENSION (not in the reference, which casts no shadow rays: SURVEY F1), defined with the
+ * reference's own Trace functions.  The ray is cast FROM THE LIGHT (1,50,0, RayTracing.cu:146) toward
+ * the shaded point lifted off the surface, P' = P + n*1e-3: the point is in shadow iff some object is hit at a
+ * distance strictly below |P' - light|.  (Casting from the light gives every shadow ray of a frame the same origin,
+ * which is what lets the GPU hoist the per-sphere terms exactly as for primary rays.)                          */
 static int shadow_blocked(const rtc_object* objs, uint32_t n, v3 point, v3 normal)
 {
     const v3 light_pos = v3_make(1.0f, 50.0f, 0.0f);
-    const v3 o = v3_add(point, v3_scale(normal, 1.0e-3f));
-    const v3 L = v3_sub(light_pos, o);
-    const float len = v3_length(L);
-    const v3 d = v3_scale(L, 1.0f / len);
+    const v3 lp = v3_sub(v3_add(point, v3_scale(normal, 1.0e-3f)), light_pos);
+    const float len = v3_length(lp);
+    const v3 d = v3_scale(lp, 1.0f / len);
     ray_terms rt;
     rt.a = v3_dot(d, d); rt.fourA = 4.0f * rt.a; rt.divTwoA = 1.0f / (2.0f * rt.a);
     for (uint32_t i = 0; i < n; ++i) {
         float t; v3 nn; int hit = 0;
-        if (objs[i].type == RTC_OBJ_SPHERE) hit = sphere_trace(&objs[i], o, d, &rt, &t, &nn);
-        else if (objs[i].type == RTC_OBJ_PLANE) hit = plane_trace(&objs[i], o, d, &t, &nn);
+        if (objs[i].type == RTC_OBJ_SPHERE) hit = sphere_trace(&objs[i], light_pos, d, &rt, &t, &nn);
+        else if (objs[i].type == RTC_OBJ_PLANE) hit = plane_trace(&objs[i], light_pos, d, &t, &nn);
         if (hit && t < len) return 1;
     }
     return 0;

@@ -100,6 +100,9 @@ struct rtc_ctx {
     struct ViewI { int32_t* p = nullptr; } d_sphere_obj, d_plane_obj;
     DevBuf<float> d_fast;      // 12 B per sphere slot (slots padded to a multiple of 4)
     DevBuf<float4> d_exact;
+    DevBuf<float> d_fast_l;    // the same hoist with the light as origin (shadow-ray extension)
+    DevBuf<float4> d_exact_l;
+    DevBuf<uint8_t> d_shadow;  // 1 byte per pixel: occluded
 
     // frame buffers
     DevBuf<float> d_hit_t;
@@ -226,8 +229,16 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
     c->last_launches = 0;
     if (record_events) CK(cudaEventRecord(c->ev[0], c->stream));
     CK(rtc::launch_hoist(c->stream, c->d_objs.p, c->d_sphere_obj.p, n_spheres, n_slots, p->cam_pos, c->d_fast.p,
-                         c->d_exact.p, c->d_counters.p, 32));
+                         c->d_exact.p, c->d_counters.p, rtc::kNumCounters));
     c->last_launches++;
+    const bool shadows = (flags & RTC_FLAG_SHADOWS) != 0 && mode != RTC_SDL && mode != RTC_RGB_NORMALS;
+    if (shadows) {
+        CK(c->d_fast_l.ensure(n_slots > 0 ? 3 * (size_t)n_slots : 12));
+        CK(c->d_exact_l.ensure(n_slots > 0 ? n_slots : 4));
+        CK(rtc::launch_hoist(c->stream, c->d_objs.p, c->d_sphere_obj.p, n_spheres, n_slots, rtc::kLightPos, c->d_fast_l.p,
+                             c->d_exact_l.p, c->d_counters.p, 0));
+        c->last_launches++;
+    }
     if (record_events) CK(cudaEventRecord(c->ev[1], c->stream));
     if (n_px > 0) {
         CK(c->d_hit_t.ensure(n_px));
@@ -242,13 +253,27 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
             const bool last = ch == n_chunks - 1;
             CK(rtc::launch_trace(c->stream, c->sm_count, fp, c->d_fast.p + 3 * (size_t)s0, c->d_exact.p + s0, c->d_sphere_obj.p + s0,
                                  sph, slots, c->d_objs.p, c->d_plane_obj.p, last ? n_planes : 0, c->d_hit_t.p,
-                                 c->d_hit_idx.p, c->d_counters.p + ch, ch > 0 ? 1 : 0));
+                                 c->d_hit_idx.p, c->d_counters.p + ch, ch > 0 ? 1 : 0, nullptr, nullptr));
             c->last_launches++;
+        }
+        if (shadows) {                                          // second pass: one ray per shaded pixel, cast from the light
+            CK(c->d_shadow.ensure(n_px));
+            for (int ch = 0; ch < n_chunks; ++ch) {
+                const int s0 = ch * rtc::kMaxSlotsPerLaunch;
+                const int slots = n_slots - s0 < rtc::kMaxSlotsPerLaunch ? n_slots - s0 : rtc::kMaxSlotsPerLaunch;
+                const int sph = n_spheres - s0 < slots ? n_spheres - s0 : slots;
+                const bool last = ch == n_chunks - 1;
+                CK(rtc::launch_trace(c->stream, c->sm_count, fp, c->d_fast_l.p + 3 * (size_t)s0, c->d_exact_l.p + s0,
+                                     c->d_sphere_obj.p + s0, sph, slots, c->d_objs.p, c->d_plane_obj.p, last ? n_planes : 0,
+                                     c->d_hit_t.p, c->d_hit_idx.p, c->d_counters.p + 32 + ch, ch > 0 ? 1 : 0, rtc::kLightPos,
+                                     c->d_shadow.p));
+                c->last_launches++;
+            }
         }
         if (record_events) CK(cudaEventRecord(c->ev[2], c->stream));
         if (mode != RTC_SDL) {
             CK(rtc::launch_shade(c->stream, fp, mode, flags, c->d_objs.p, (int)c->objs.size(), c->d_hit_t.p,
-                                 c->d_hit_idx.p, d_color, d_glyph));
+                                 c->d_hit_idx.p, shadows ? c->d_shadow.p : nullptr, d_color, d_glyph));
             c->last_launches++;
         }
         if (record_events) CK(cudaEventRecord(c->ev[3], c->stream));
@@ -326,6 +351,7 @@ void rtc_destroy(rtc_ctx* c)
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     c->d_scene.release(); c->d_fast.release(); c->d_exact.release();
+    c->d_fast_l.release(); c->d_exact_l.release(); c->d_shadow.release();
     c->d_hit_t.release(); c->d_hit_idx.release(); c->d_color.release(); c->d_glyph.release(); c->d_out[0].release(); c->d_out[1].release();
     c->d_desc.release(); c->d_counters.release(); c->d_total.release(); c->d_sink.release();
     c->h_total.release(); c->h_out[0].release(); c->h_out[1].release(); c->h_scene[0].release(); c->h_scene[1].release();

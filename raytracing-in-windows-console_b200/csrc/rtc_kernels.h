@@ -21,12 +21,14 @@ cudaError_t launch_hoist(cudaStream_t st, const rtc_object* objs, const int32_t*
 cudaError_t launch_trace(cudaStream_t st, int n_ctas, const FrameParams& fp, const float* g_fast, const float4* g_exact,
                          const int32_t* sphere_obj, int n_spheres, int n_slots, const rtc_object* objs,
                          const int32_t* plane_obj, int n_planes, float* hit_t, int32_t* hit_idx,
-                         unsigned int* tile_counter, int carry_in);
+                         unsigned int* tile_counter, int carry_in, const float* light /* NULL: primary rays */,
+                         uint8_t* shadow);
+constexpr float kLightPos[3] = {1.0f, 50.0f, 0.0f};            // the reference's hard-coded light (RayTracing.cu:146)
 
 // kernel 2 (rtc_shade.cu)
 cudaError_t launch_shade(cudaStream_t st, const FrameParams& fp, int mode, uint32_t flags,
                          const rtc_object* objs, int n_objs, const float* hit_t, const int32_t* hit_idx,
-                         uint8_t* color, uint8_t* glyph);
+                         const uint8_t* shadow /* NULL: every point is lit */, uint8_t* color, uint8_t* glyph);
 
 // kernel 3 (rtc_encode.cu)
 cudaError_t configure_encode();

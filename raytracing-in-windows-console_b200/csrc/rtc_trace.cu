@@ -141,6 +141,7 @@ __device__ __noinline__ void exact_group(const int32_t* __restrict__ sphere_obj,
         const float4 e = s.exact[j];
         const float dx = s.dirx[slot], dy = s.diry[slot], dz = s.dirz[slot];
         const float best = s.best_t[slot];
+        if (best < 0.0f) continue;                              // inactive ray (shadow pass: no primary hit to shade)
         {
             // t_ref ~ (-s - sqrt(D))/a with a = 1 +- 8u, |s1 - s| <= 6u|oc|, and
             // D_ref <= s1^2 - c + 23u(|oc|^2 + |c|), so t_lb <= t_ref (DESIGN.md "reject bound").
@@ -162,12 +163,21 @@ __device__ __noinline__ void exact_group(const int32_t* __restrict__ sphere_obj,
     }
 }
 
+// SHADOW = false: primary rays from the camera (hit_t / hit_idx are the outputs).
+// SHADOW = true : the shadow-ray EXTENSION (the reference casts none).  One ray per shaded pixel, cast FROM
+//   THE LIGHT (1,50,0) toward the shaded point P' = P + n*1e-3: all shadow rays then share their origin exactly like
+//   the primary rays share the camera, so the same hoist, the same packed filter and the same exact path apply
+//   unchanged (the "camera" of this launch is the light).  A pixel is in shadow iff some object is hit at a distance
+//   strictly below |P' - light| -- the nearest-hit machinery with the running best initialised to that length and
+//   no object.  hit_t / hit_idx are INPUTS here; the output is one byte per pixel in `shadow`.
+template <bool SHADOW>
 __global__ void __launch_bounds__(kThreads, 1)
 trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float4* __restrict__ g_exact,
              const int32_t* __restrict__ sphere_obj, int n_spheres, int n_slots,
              const rtc_object* __restrict__ objs, const int32_t* __restrict__ plane_obj, int n_planes,
              float* __restrict__ hit_t, int32_t* __restrict__ hit_idx, unsigned int* __restrict__ tile_counter,
-             int carry_in /* 1: continue from hit_t/hit_idx (sphere list chunking) */)
+             int carry_in /* 1: continue from hit_t/hit_idx (sphere list chunking) */,
+             float lx, float ly, float lz, uint8_t* __restrict__ shadow)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem s = carve(smem_raw, n_slots);
@@ -183,8 +193,9 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
     const uint32_t tiles_x = (W + kTile - 1) / kTile, tiles_y = (rows + kTile - 1) / kTile;
     const uint32_t n_tiles = tiles_x * tiles_y;
     const int n_groups = n_slots >> 2;
-    const V3 o = v3(fp.cam[0], fp.cam[1], fp.cam[2]);
-    const uint32_t lx = lane & 15u, ly = lane >> 4;
+    const V3 cam = v3(fp.cam[0], fp.cam[1], fp.cam[2]);
+    const V3 o = SHADOW ? v3(lx, ly, lz) : cam;                 // common origin of this launch's rays
+    const uint32_t px = lane & 15u, py = lane >> 4;
     const f32x2 ZERO2 = pack2(0.0f, 0.0f);
     const uint32_t fast_base = (uint32_t)__cvta_generic_to_shared(s.fast);
 
@@ -194,27 +205,61 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= n_tiles) break;
         const uint32_t ty = tile / tiles_x, tx = tile - ty * tiles_x;
-        const uint32_t col = tx * kTile + lx;
+        const uint32_t col = tx * kTile + px;
         const uint32_t colc = col < W ? col : W - 1u;     // clamp: out-of-frame lanes trace a duplicate ray
 
         float ex[kRays], ey[kRays], ez[kRays];            // ray direction scaled by 2^64 (exact)
 #pragma unroll
         for (int r = 0; r < kRays; ++r) {
-            uint32_t row = fp.row0 + ty * kTile + ly + 2u * r;
+            uint32_t row = fp.row0 + ty * kTile + py + 2u * r;
             if (row >= fp.row1) row = fp.row1 - 1u;
-            const V3 d = initial_direction(fp, row, colc);
+            V3 d = initial_direction(fp, row, colc);
+            float bt = 99999999.f;                                        // RayTracing.h:21
+            int bi = -1;
+            const size_t pix = (size_t)(row - fp.row0) * W + colc;
+            if (!SHADOW) {
+                if (carry_in) { bt = hit_t[pix]; bi = hit_idx[pix]; }
+            } else {
+                const float t = hit_t[pix];
+                const int idx = hit_idx[pix];
+                bt = -1.0f;                                               // inactive unless there is a point to shade
+                if (t <= fp.far_dist && idx >= 0 && !(carry_in && shadow[pix])) {
+                    const rtc_object ob = objs[idx];
+                    const V3 point = vadd(cam, vscale(d, t));             // RayTracing.cu:149
+                    V3 n;
+                    if (ob.type == RTC_OBJ_SPHERE)                        // Sphere.cu:67
+                        n = vnormalize(vsub(point, v3(ob.center[0], ob.center[1], ob.center[2])));
+                    else
+                        n = v3(ob.normal[0], ob.normal[1], ob.normal[2]); // Plane.cu:72
+                    n = vnormalize(n);                                    // RayTracing.cu:129
+                    const V3 lp = vsub(vadd(point, vscale(n, 1.0e-3f)), o);
+                    const float len = vlength(lp);
+                    d = vscale(lp, dvd(1.0f, len));
+                    bt = len;
+                } else {
+                    d = v3(0.0f, 0.0f, 0.0f);
+                }
+            }
             ex[r] = d.x * RTC_TWO64; ey[r] = d.y * RTC_TWO64; ez[r] = d.z * RTC_TWO64;
             const int slot = r * kThreads + tid;
             s.dirx[slot] = d.x; s.diry[slot] = d.y; s.dirz[slot] = d.z;
             s.div2A[slot] = dvd(1.0f, mul(2.0f, vdot(d, d)));             // RayTracing.cu:91,93
-            float bt = 99999999.f;                                        // RayTracing.h:21
-            int bi = -1;
-            if (carry_in) {
-                const size_t pix = (size_t)(row - fp.row0) * W + colc;
-                bt = hit_t[pix]; bi = hit_idx[pix];
-            }
             s.best_t[slot] = bt;
             s.best_idx[slot] = bi;
+        }
+
+        if (SHADOW) {                                           // tiles without a shaded pixel need no shadow rays
+            bool any = false;
+#pragma unroll
+            for (int r = 0; r < kRays; ++r) any |= s.best_t[r * kThreads + tid] >= 0.0f;
+            if (!__any_sync(0xffffffffu, any)) {
+#pragma unroll
+                for (int r = 0; r < kRays; ++r) {
+                    const uint32_t row = fp.row0 + ty * kTile + py + 2u * r;
+                    if (row < fp.row1 && col < W && !carry_in) shadow[(size_t)(row - fp.row0) * W + col] = 0;
+                }
+                continue;
+            }
         }
 
         // ---- hot loop: 4 spheres (2 packed pairs) x 8 rays per iteration, operand-major ----------
@@ -270,6 +315,7 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
                 float t;
                 const int slot = r * kThreads + tid;
                 const V3 d = v3(s.dirx[slot], s.diry[slot], s.dirz[slot]);
+                if (SHADOW && s.best_t[slot] < 0.0f) continue;
                 if (plane_trace(pl, o, d, t)) {
                     const float best = s.best_t[slot];
                     if (t < best || (t == best && oi < s.best_idx[slot])) { s.best_t[slot] = t; s.best_idx[slot] = oi; }
@@ -280,12 +326,17 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
         // ---- hit records ------------------------------------------------------------------
 #pragma unroll
         for (int r = 0; r < kRays; ++r) {
-            const uint32_t row = fp.row0 + ty * kTile + ly + 2u * r;
+            const uint32_t row = fp.row0 + ty * kTile + py + 2u * r;
             if (row < fp.row1 && col < W) {
                 const size_t pix = (size_t)(row - fp.row0) * W + col;
                 const int slot = r * kThreads + tid;
-                hit_t[pix] = s.best_t[slot];
-                hit_idx[pix] = s.best_idx[slot];
+                if (!SHADOW) {
+                    hit_t[pix] = s.best_t[slot];
+                    hit_idx[pix] = s.best_idx[slot];
+                } else {
+                    const bool occluded = s.best_idx[slot] != -1;
+                    if (!carry_in || occluded) shadow[pix] = occluded ? 1 : 0;
+                }
             }
         }
     }
@@ -293,7 +344,9 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
 
 cudaError_t configure_trace()   // per device, once per context
 {
-    return cudaFuncSetAttribute(trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(trace_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(trace_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
 size_t trace_smem_bytes(int n_slots)
@@ -306,6 +359,7 @@ cudaError_t launch_hoist(cudaStream_t st, const rtc_object* objs, const int32_t*
                          unsigned int* counters, int n_counters)
 {
     const int n = n_slots > n_counters ? n_slots : n_counters;
+    if (n <= 0) return cudaSuccess;
     hoist_kernel<<<(n + 255) / 256, 256, 0, st>>>(objs, sphere_obj, n_spheres, n_slots, cam[0], cam[1], cam[2],
                                                   sph_fast, sph_exact, counters, n_counters);
     return cudaGetLastError();
@@ -314,11 +368,16 @@ cudaError_t launch_hoist(cudaStream_t st, const rtc_object* objs, const int32_t*
 cudaError_t launch_trace(cudaStream_t st, int n_ctas, const FrameParams& fp, const float* g_fast, const float4* g_exact,
                          const int32_t* sphere_obj, int n_spheres, int n_slots, const rtc_object* objs,
                          const int32_t* plane_obj, int n_planes, float* hit_t, int32_t* hit_idx,
-                         unsigned int* tile_counter, int carry_in)
+                         unsigned int* tile_counter, int carry_in, const float* light, uint8_t* shadow)
 {
-    trace_kernel<<<n_ctas, kThreads, trace_smem_bytes(n_slots), st>>>(fp, g_fast, g_exact, sphere_obj, n_spheres, n_slots,
-                                                                      objs, plane_obj, n_planes, hit_t, hit_idx,
-                                                                      tile_counter, carry_in);
+    if (light)
+        trace_kernel<true><<<n_ctas, kThreads, trace_smem_bytes(n_slots), st>>>(
+            fp, g_fast, g_exact, sphere_obj, n_spheres, n_slots, objs, plane_obj, n_planes, hit_t, hit_idx, tile_counter,
+            carry_in, light[0], light[1], light[2], shadow);
+    else
+        trace_kernel<false><<<n_ctas, kThreads, trace_smem_bytes(n_slots), st>>>(
+            fp, g_fast, g_exact, sphere_obj, n_spheres, n_slots, objs, plane_obj, n_planes, hit_t, hit_idx, tile_counter,
+            carry_in, 0.f, 0.f, 0.f, nullptr);
     return cudaGetLastError();
 }
 

@@ -290,10 +290,23 @@ def test_shadow_extension(ctx, oracle, rtc):
 
 
 def test_many_spheres_chunked(ctx, oracle, rtc):
-    """More spheres than one shared-memory chunk (8192): multi-launch carry of the running best."""
+    """More spheres than one shared-memory chunk (4096): multi-launch carry of the running best (and, for the
+    shadow pass, of the occlusion mask)."""
     objs = scenes.random_spheres(9000, 31)
     p = rtc.camera_params(49, 20, (0, 0, -120), (0, PI32, 0), 1.0 / 48)
     check_frame(ctx, oracle, objs, p, RGB_PIXEL)
+    check_frame(ctx, oracle, objs, p, RGB_PIXEL, flags=FLAG_SHADOWS)
+
+
+def test_shadow_pass_config2(ctx, oracle):
+    """BASELINE config 2 (1921x1080, 64 spheres + plane, primary + shadow rays): the light-origin shadow pass
+    (trace_kernel<true>: packed filter + exact path) against the oracle's definition, whole frame, two modes."""
+    objs = scenes.config_scene("config2_1080p_64")
+    p = scenes.config_camera("config2_1080p_64")
+    s_on = check_frame(ctx, oracle, objs, p, RGB_PIXEL, flags=FLAG_SHADOWS)
+    s_off = check_frame(ctx, oracle, objs, p, RGB_PIXEL)
+    assert not np.array_equal(s_on, s_off)
+    check_frame(ctx, oracle, objs, p, BIT_ASCII, flags=FLAG_SHADOWS)
 
 
 def test_pipelined_submit_collect(ctx, rtc):
