@@ -45,6 +45,15 @@ def parse_args():
     return ap.parse_args()
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of our kernels from the committed ncu --set full captures (profiles/)."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    try:
+        return json.load(open(path))
+    except Exception:
+        return {}
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -446,7 +455,9 @@ def run_ours(args):
             measured_ffma = measured_ffma2 = None
         _, n_stream = ctx.frame_ansi_device()
         line["roofline"] = {"bound": "fp32", "kernel": "trace_kernel", "achieved": achieved, "peak": fp32_peak,
-                            "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": None,
+                            "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+                            "traffic": (ncu_traffic().get("trace_kernel", {}).get("traffic") if name == "config3_4k_1024" else None),
+                            "traffic_note": "DRAM bytes per launch from profiles/r01_ncu_traffic.json (ncu --set full): the kernel is FP32-pipe bound, 0.1 % of HBM bandwidth",
                             "peak_source": "%d SMs x 128 lanes x 2 FLOP x %.0f MHz (%s sm_max_mhz); not in MEASURED_PEAKS.json, which has HBM and bf16 tensor only"
                                            % (sm_count, pk["sm_max_mhz"], pk["source"]),
                             "algorithmic_flops_per_launch": 7.0 * frame_rays * n_spheres, "launches_in_kernel_ms": n_passes, "kernel_ms": trace_ms,
@@ -461,7 +472,8 @@ def run_ours(args):
             line["roofline_encoder"] = {"bound": "hbm", "kernel": "count_kernel + emit_kernel (2 launches)",
                                         "workload": "config5_encode_8k: 7681x4320, i.i.d. random RGB",
                                         "achieved": st_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": st_gbs / pk["hbm_gbs"],
-                                        "traffic": None, "algorithmic_bytes_per_launch": st_in + st_out, "kernel_ms": st_ms,
+                                        "traffic": sum(ncu_traffic().get(k, {}).get("traffic", 0.0) for k in ("count_kernel<3>", "emit_kernel<3, 0>")) or None,
+                                        "algorithmic_bytes_per_launch": st_in + st_out, "kernel_ms": st_ms,
                                         "peak_source": pk["source"] + " (MEASURED_PEAKS.json hbm_gbs)"}
         except Exception as e:
             line["roofline_encoder"] = {"error": repr(e)}
