@@ -15,7 +15,7 @@ from ._types import (BIT_ASCII, BIT_PIXEL, FLAG_SHADOWS, FLAG_UPDATE_REF_LAUNCH_
                      mode_bpp, mode_cell, mode_has_glyph, obj_ptr)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librtc_b200.so")
+LIB_PATH = os.environ.get("RTC_B200_LIB") or os.path.join(_HERE, "librtc_b200.so")   # override: kernel experiments
 
 # every symbol include/rtc.h declares (tests check the library exports all of them)
 EXPORTS = [

@@ -9,7 +9,14 @@ namespace rtc {
 
 struct FrameParams;
 
-constexpr int kMaxSlotsPerLaunch = 4096;   // sphere slots resident in shared memory per trace launch
+#ifndef RTC_TRACE_THREADS
+// Threads of the persistent ray-kernel CTA (one CTA per SM).  Measured on config 3 / config 4 (trace ms):
+// 512: 1.268 / 18.52, 640: 1.240 / 18.32, 768: 1.206 / 17.86, 896: 1.208 / 17.95, 1024: 1.208 / 18.23 (register cap
+// 64 -> spills; more sphere chunks) -- profiles/r01_trace_kernel_ncu.md.
+#define RTC_TRACE_THREADS 768
+#endif
+// sphere slots resident in shared memory per trace launch: 28 B per slot next to 192 B of ray state per thread
+constexpr int kMaxSlotsPerLaunch = ((227 * 1024 - RTC_TRACE_THREADS * 192) / 28) & ~3;
 constexpr int kNumCounters = 64;           // per-frame device counters zeroed by the hoist kernel
 
 // kernel 0 / 1 (rtc_trace.cu)

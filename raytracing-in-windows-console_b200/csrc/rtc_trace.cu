@@ -7,8 +7,9 @@
 //   * All primary rays share the origin (RayTracing.cu:195), so oc = origin - centre and
 //     c = |oc|^2 - r^2 are per-sphere, per-frame constants: kernel 0 hoists them (bit-identical
 //     to what the reference recomputes per ray).
-//   * Kernel 1 is persistent: one 512-thread CTA per SM keeps the whole sphere list in shared
-//     memory and walks 16x16-pixel screen tiles, one tile per warp, 8 rays per thread.
+//   * Kernel 1 is persistent: one 768-thread CTA per SM keeps the sphere list (up to 3032 spheres per
+//     launch; longer lists are chunked) in shared memory and walks 16x16-pixel screen tiles, one tile
+//     per warp, 8 rays per thread.
 //   * The inner loop tests TWO spheres against one ray per packed instruction (FMUL2/FFMA2).
 //     Measured on B200: an FFMA2 only sustains 1 per 2 cycles when at most one operand pair is
 //     fresh (register-bank limit), and every ALU-pipe instruction (FMNMX3, FSETP, ...) costs
@@ -75,7 +76,7 @@ hoist_kernel(const rtc_object* __restrict__ objs, const int32_t* __restrict__ sp
 
 // ---- kernel 1: trace --------------------------------------------------------------------
 constexpr int kRays = 8;            // rays per thread
-constexpr int kThreads = 512;       // 16 warps, one CTA per SM
+constexpr int kThreads = RTC_TRACE_THREADS;   // 24 warps, one CTA per SM
 constexpr int kTile = 16;           // warp tile = 16 x 16 pixels
 constexpr int kStateFloats = 6 * kRays * kThreads;   // best_t, best_idx, div2A, dir x/y/z
 

@@ -290,7 +290,7 @@ def test_shadow_extension(ctx, oracle, rtc):
 
 
 def test_many_spheres_chunked(ctx, oracle, rtc):
-    """More spheres than one shared-memory chunk (4096): multi-launch carry of the running best (and, for the
+    """More spheres than one shared-memory chunk (3032): multi-launch carry of the running best (and, for the
     shadow pass, of the occlusion mask)."""
     objs = scenes.random_spheres(9000, 31)
     p = rtc.camera_params(49, 20, (0, 0, -120), (0, PI32, 0), 1.0 / 48)
