@@ -37,7 +37,9 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config3_4k_1024")
     ap.add_argument("--mode", default="RGB_PIXEL")
-    ap.add_argument("--gather", default="ipc", choices=["nccl", "ipc"])
+    ap.add_argument("--gather", default="host", choices=["host", "nccl", "ipc"],
+                    help="N > 1: host = every rank encodes its band and copies its piece of the stream into one shared pinned "
+                         "host frame (no data-path collective); ipc / nccl = planes gathered to GPU 0 over NVLink, encoded there")
     ap.add_argument("--orbit", type=int, default=0, help="camera orbit of this many frames (config 4: 120); 0 = fixed camera")
     ap.add_argument("--shadows", action="store_true", help="shadow-ray extension on (second, light-origin trace pass)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -290,16 +292,19 @@ def run_ours(args):
         # Row bands: every rank traces + shades its band straight into (ipc) or followed by NCCL send/recv into (nccl)
         # rank 0's frame planes; rank 0 encodes the assembled frame.  Rank 0 also pays for the encoder, so it gets a
         # smaller band: the deficit (in rows) is measured on rank 0 from one whole frame's stage timings.
-        hdr = [0.0]
-        if rank == 0:
-            for _ in range(3):
-                ctx.render(p, mode)
-            torch.cuda.synchronize()
-            t = ctx.timings()
-            hdr = [t["encode_ms"] / max(1e-9, (t["trace_ms"] + t["shade_ms"]) / y)]
-        dist.broadcast_object_list(hdr, src=0)
-        deficit = float(hdr[0])
-        renderer = multigpu.BandRenderer(ctx, dist, rank, world, x, y, mode, gather=args.gather, deficit_rows=deficit)
+        if args.gather == "host":
+            renderer = multigpu.HostAssembledRenderer(ctx, dist, rank, world, x, y, mode)
+        else:
+            hdr = [0.0]
+            if rank == 0:
+                for _ in range(3):
+                    ctx.render(p, mode)
+                torch.cuda.synchronize()
+                t = ctx.timings()
+                hdr = [t["encode_ms"] / max(1e-9, (t["trace_ms"] + t["shade_ms"]) / y)]
+            dist.broadcast_object_list(hdr, src=0)
+            deficit = float(hdr[0])
+            renderer = multigpu.BandRenderer(ctx, dist, rank, world, x, y, mode, gather=args.gather, deficit_rows=deficit)
 
         def step():
             return renderer.step(next_cam(), rflags)
@@ -382,7 +387,8 @@ def run_ours(args):
     else:
         # Pipelined like rtc_submit / rtc_collect: frame k+1 is enqueued on every rank before rank 0 waits for frame k's
         # stream length and copies the stream to pinned host memory on a separate copy stream.
-        host = [torch.empty(cap, dtype=torch.uint8, pin_memory=True) for _ in range(2)] if rank == 0 else None
+        host = ([torch.empty(cap, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+                if (rank == 0 and args.gather != "host") else None)
         copy_stream = torch.cuda.Stream()
         done = [torch.cuda.Event(), torch.cuda.Event()]
         h_total = torch.zeros(2, dtype=torch.int64, pin_memory=True) if rank == 0 else None
@@ -405,6 +411,13 @@ def run_ours(args):
             copy_stream.synchronize()
             return n
 
+        if args.gather == "host":
+            def submit():                                  # noqa: F811
+                ctx.set_objects(objs)
+                return renderer.submit(next_cam(), rflags)
+
+            def collect(sl):                               # noqa: F811
+                return renderer.collect()[1]
         sync_all()
         prev = submit()
         t0 = time.perf_counter()
@@ -419,11 +432,22 @@ def run_ours(args):
         tt = torch.tensor([(t1 - t0) * 1e3 / args.steps], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_ms = float(tt.item())
-        e2e = {"value": frame_rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms,
+        host_breakdown = None
+        if args.gather == "host":
+            kk = max(1, renderer.k_col)
+            host_breakdown = {"wait_gpu_ms": renderer.t_wait_gpu * 1e3 / kk, "wait_lengths_ms": renderer.t_wait_len * 1e3 / kk,
+                              "d2h_ms": renderer.t_copy * 1e3 / kk, "wait_ranks_ms": renderer.t_wait_done * 1e3 / kk,
+                              "submit_step_ms": getattr(renderer, "t_submit_step", 0.0) * 1e3 / kk,
+                              "submit_rest_ms": getattr(renderer, "t_submit_rest", 0.0) * 1e3 / kk}
+        e2e = {"rank0_collect_breakdown": host_breakdown,"value": frame_rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": int(objs.nbytes + 96) * world, "d2h_bytes_per_step": int(nbytes + 8),
-               "api": "per rank rtc_scene_set_objects + rtc_trace_band, bands gathered to GPU 0, rtc_encode, stream copied to pinned host memory (pipelined two deep)"}
+               "api": ("per rank rtc_scene_set_objects + rtc_trace_band + rtc_encode_band, every rank copies its piece of the stream into one shared pinned host frame (pipelined two deep)"
+                       if args.gather == "host" else
+                       "per rank rtc_scene_set_objects + rtc_trace_band, bands gathered to GPU 0, rtc_encode, stream copied to pinned host memory (pipelined two deep)")}
 
     if rank != 0:
+        if renderer is not None:
+            renderer.close()
         if dist is not None:
             dist.destroy_process_group()
         return
@@ -491,8 +515,11 @@ def run_ours(args):
                 line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
     else:
         # hoist + trace + shade per rank, + encode on rank 0
-        line["gpu_launches"] = int((3 * world + 2) * args.steps)
+        # hoist + trace + shade per rank; count + emit per rank (host) or on rank 0 only (ipc / nccl)
+        line["gpu_launches"] = int(((5 * world) if args.gather == "host" else (3 * world + 2)) * args.steps)
     print(json.dumps(line))
+    if renderer is not None:
+        renderer.close()
     if dist is not None:
         dist.destroy_process_group()
 

@@ -200,6 +200,15 @@ RTC_API int rtc_trace_band(rtc_ctx* ctx, const rtc_params* params, rtc_mode mode
 RTC_API int rtc_encode(rtc_ctx* ctx, const uint8_t* dev_color, const uint8_t* dev_glyph,
                        uint32_t x, uint32_t y, rtc_mode mode, char* dev_out, size_t cap,
                        unsigned long long* dev_total);
+/* The same for a ROW BAND of a frame, so that every GPU can encode its own band and the per-band streams simply
+ * concatenate to the frame's stream: `rows` rows starting at dev_color.  continues = 0: the band starts the frame
+ * (its first cell always emits, as in rtc_encode).  continues != 0: the band continues a frame -- the colour key of
+ * the cell stored immediately BEFORE dev_color (dev_color - bpp; the last cell of the previous row, which the caller
+ * traces as one extra context row: rtc_trace_band(row0 - 1, ...)) decides whether the band's first cell emits, exactly
+ * as MinimizeRGB carries latestColor across rows (RayTracingManager.cu:262-301).                                   */
+RTC_API int rtc_encode_band(rtc_ctx* ctx, const uint8_t* dev_color, const uint8_t* dev_glyph, uint32_t x,
+                            uint32_t rows, rtc_mode mode, int continues, char* dev_out, size_t cap,
+                            unsigned long long* dev_total);
 RTC_API size_t rtc_encode_capacity(uint32_t x, uint32_t y, rtc_mode mode);
 RTC_API uint32_t rtc_mode_bpp(rtc_mode mode);
 RTC_API uint32_t rtc_mode_has_glyph(rtc_mode mode);

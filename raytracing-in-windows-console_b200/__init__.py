@@ -23,7 +23,7 @@ EXPORTS = [
     "rtc_resize", "rtc_scene_clear", "rtc_scene_add_sphere", "rtc_scene_add_plane", "rtc_scene_set_objects",
     "rtc_scene_get_objects", "rtc_scene_count", "rtc_update_objects", "rtc_render", "rtc_frame_ansi",
     "rtc_frame_ansi_device", "rtc_frame_color", "rtc_frame_hits", "rtc_update", "rtc_submit", "rtc_collect", "rtc_last_timings",
-    "rtc_trace_band", "rtc_encode", "rtc_encode_capacity", "rtc_mode_bpp", "rtc_mode_has_glyph",
+    "rtc_trace_band", "rtc_encode", "rtc_encode_band", "rtc_encode_capacity", "rtc_mode_bpp", "rtc_mode_has_glyph",
     "rtc_ipc_export", "rtc_ipc_open", "rtc_ipc_close", "rtc_camera_params", "rtc_fp32_peak",
 ]
 
@@ -78,6 +78,7 @@ def load_library(build_if_missing=True):
     L.rtc_last_timings.argtypes = [vp, vp]
     L.rtc_trace_band.argtypes = [vp, vp, i32, u32, u32, u32, vp, vp]
     L.rtc_encode.argtypes = [vp, vp, vp, u32, u32, i32, vp, sz, vp]
+    L.rtc_encode_band.argtypes = [vp, vp, vp, u32, u32, i32, i32, vp, sz, vp]
     L.rtc_ipc_export.argtypes = [vp, vp, vp]
     L.rtc_ipc_open.argtypes = [vp, vp, c.POINTER(vp)]
     L.rtc_ipc_close.argtypes = [vp, vp]
@@ -234,6 +235,10 @@ class Context:
     def encode(self, dev_color, dev_glyph, x, y, mode, dev_out, cap, dev_total):
         _check(self.L.rtc_encode(self._h, ctypes.c_void_p(dev_color), ctypes.c_void_p(dev_glyph or 0), x, y, mode,
                                  ctypes.c_void_p(dev_out), cap, ctypes.c_void_p(dev_total)))
+
+    def encode_band(self, dev_color, dev_glyph, x, rows, mode, continues, dev_out, cap, dev_total):
+        _check(self.L.rtc_encode_band(self._h, ctypes.c_void_p(dev_color), ctypes.c_void_p(dev_glyph or 0), x, rows, mode,
+                                      1 if continues else 0, ctypes.c_void_p(dev_out), cap, ctypes.c_void_p(dev_total)))
 
     def ipc_export(self, dev_ptr):
         h = (ctypes.c_ubyte * 64)()

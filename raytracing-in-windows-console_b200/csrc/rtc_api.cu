@@ -662,6 +662,27 @@ int rtc_encode(rtc_ctx* c, const uint8_t* dev_color, const uint8_t* dev_glyph, u
     return RTC_OK;
 }
 
+int rtc_encode_band(rtc_ctx* c, const uint8_t* dev_color, const uint8_t* dev_glyph, uint32_t x, uint32_t rows, rtc_mode mode,
+                    int continues, char* dev_out, size_t cap, unsigned long long* dev_total)
+{
+    if (!c) return fail(RTC_ERR_INVALID, "ctx is NULL");
+    if (!dev_out || !dev_total) return fail(RTC_ERR_INVALID, "NULL output");
+    if (x < 1) return fail(RTC_ERR_INVALID, "invalid console width %u", x);
+    if (mode < RTC_BIT_ASCII || mode > RTC_SDL) return fail(RTC_ERR_INVALID, "invalid rendering mode %d", mode);
+    if (mode != RTC_SDL && x > 1 && rows > 0 && !dev_color) return fail(RTC_ERR_INVALID, "dev_color is NULL");
+    if ((uint64_t)(x - 1u) * rows >= (1ull << 31)) return fail(RTC_ERR_CAPACITY, "band too large");
+    CK(cudaSetDevice(c->device));
+    if (rows == 0) {                                            // an empty band contributes an empty stream
+        CK(cudaMemsetAsync(dev_total, 0, sizeof(unsigned long long), c->stream));
+        return RTC_OK;
+    }
+    int rc = encode_scratch(c, (uint64_t)(x - 1u) * rows);
+    if (rc) return rc;
+    CK(rtc::launch_encode(c->stream, dev_color, dev_glyph, x, rows, mode, dev_out, cap, dev_total, c->d_desc.p, c->d_desc.cap,
+                          c->enc_parity, continues != 0));
+    return RTC_OK;
+}
+
 int rtc_ipc_export(rtc_ctx* c, void* dev_ptr, unsigned char handle_out[64])
 {
     if (!c || !dev_ptr || !handle_out) return fail(RTC_ERR_INVALID, "NULL argument");

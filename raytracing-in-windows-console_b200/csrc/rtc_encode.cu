@@ -77,6 +77,8 @@ struct EncGeom {
                                      // is < W <= 2^(shift-31), so n * error < 2^shift for every n < 2^31)
     uint32_t n_cells;
     uint32_t fast_hi_emit, fast_hi_count;   // lanes with cell-1 < fast_hi may load their key window unclamped
+    uint32_t force_first;            // 1: cell 0 starts the frame and always emits; 0: the plane continues a frame and
+                                     //    the cell stored just before it is cell 0's predecessor (row-band encoding)
     unsigned long long first_w, last_w;     // first / last 32-bit word holding plane bytes
 };
 template <int BPP, int C> struct EncIn {
@@ -152,12 +154,12 @@ __device__ __forceinline__ void load_keys(const uint8_t* __restrict__ color, con
 
 // Bit i of the result: cell i emits its whole escape sequence (its colour key differs from its predecessor's).
 template <int C>
-__device__ __forceinline__ uint32_t full_cells(const uint32_t (&key)[C + 1], uint32_t cell, int n_valid)
+__device__ __forceinline__ uint32_t full_cells(const uint32_t (&key)[C + 1], uint32_t cell, int n_valid, uint32_t force_first)
 {
     uint32_t fm = 0;
 #pragma unroll
     for (int i = 0; i < C; ++i) fm |= (key[i + 1] != key[i]) ? (1u << i) : 0u;
-    fm |= cell == 0u ? 1u : 0u;                                 // first cell of the frame always emits
+    fm |= (cell == 0u && force_first) ? 1u : 0u;                // first cell of the frame always emits
     return fm & ((1u << n_valid) - 1u);
 }
 
@@ -185,7 +187,7 @@ count_kernel(const uint8_t* __restrict__ color, const EncGeom g, uint32_t* __res
     if (n_valid > 0) {
         uint32_t key[kCntC + 1];
         load_keys<BPP, kCntC, true>(color, g, g.fast_hi_count, cell, key);
-        const uint32_t fm = full_cells<kCntC>(key, cell, n_valid);
+        const uint32_t fm = full_cells<kCntC>(key, cell, n_valid, g.force_first);
         const uint32_t newlines = row_of(g, cell + (uint32_t)n_valid) - row_of(g, cell);   // row ends in [cell, cell + n_valid)
         len = (uint32_t)n_valid + (CS - 1u) * __popc(fm) + newlines;
     }
@@ -320,7 +322,7 @@ emit_kernel(const uint8_t* __restrict__ color, const uint8_t* __restrict__ glyph
     uint32_t key[kEncC + 1], fm = 0, nm = 0, len = 0;
     if (n_valid > 0) {
         load_keys<BPP, kEncC, false>(color, g, g.fast_hi_emit, cell, key);
-        fm = full_cells<kEncC>(key, cell, n_valid);
+        fm = full_cells<kEncC>(key, cell, n_valid, g.force_first);
         const uint32_t col = cell - row_of(g, cell) * g.W;
         if (g.W >= (uint32_t)kEncC) {                           // at most one row end among kEncC consecutive cells
             const uint32_t d = g.W - 1u - col;
@@ -384,7 +386,7 @@ emit_kernel(const uint8_t* __restrict__ color, const uint8_t* __restrict__ glyph
 }
 
 template <int BPP>
-static EncGeom make_geom(const uint8_t* color, uint32_t W, uint32_t n_cells)
+static EncGeom make_geom(const uint8_t* color, uint32_t W, uint32_t n_cells, bool continues)
 {
     EncGeom g;
     uint32_t l = 0;
@@ -396,7 +398,8 @@ static EncGeom make_geom(const uint8_t* color, uint32_t W, uint32_t n_cells)
     g.fast_hi_emit = n_cells >= me ? n_cells - me : 0u;
     g.fast_hi_count = n_cells >= mc ? n_cells - mc : 0u;
     const unsigned long long base = (unsigned long long)reinterpret_cast<uintptr_t>(color);
-    g.first_w = base & ~3ull;
+    g.force_first = continues ? 0u : 1u;
+    g.first_w = (base - (continues ? (unsigned long long)BPP : 0ull)) & ~3ull;   // the predecessor cell is readable
     g.last_w = (base + (unsigned long long)n_cells * BPP - 1ull) & ~3ull;
     return g;
 }
@@ -437,7 +440,7 @@ size_t encode_state_bytes(uint64_t n_cells)
 
 cudaError_t launch_encode(cudaStream_t st, const uint8_t* color, const uint8_t* glyph, uint32_t x, uint32_t y,
                           int mode, char* out, size_t cap, unsigned long long* total, void* scratch, size_t scratch_bytes,
-                          uint32_t parity)
+                          uint32_t parity, bool continues)
 {
     if (mode == RTC_SDL) {
         newline_kernel<<<(y + 255) / 256, 256, 0, st>>>(out, y, cap, total);
@@ -464,7 +467,7 @@ cudaError_t launch_encode(cudaStream_t st, const uint8_t* color, const uint8_t* 
     uint32_t* warp_excl = tile_len + ((t_max + 4u) & ~3u);
     const bool has_glyph = (mode == RTC_BIT_ASCII || mode == RTC_RGB_ASCII) && glyph != nullptr;
     const bool bit8 = (mode == RTC_BIT_ASCII || mode == RTC_BIT_PIXEL);
-    const EncGeom g = bit8 ? make_geom<1>(color, W, n_cells) : make_geom<3>(color, W, n_cells);
+    const EncGeom g = bit8 ? make_geom<1>(color, W, n_cells, continues) : make_geom<3>(color, W, n_cells, continues);
     const uint32_t n_cnt = (n_tiles + kCntTiles - 1) / kCntTiles;
     if (bit8) count_kernel<1><<<n_cnt, kEncThreads, 0, st>>>(color, g, tile_len, warp_excl, group_len, super_len, zero_next, acc_n);
     else count_kernel<3><<<n_cnt, kEncThreads, 0, st>>>(color, g, tile_len, warp_excl, group_len, super_len, zero_next, acc_n);

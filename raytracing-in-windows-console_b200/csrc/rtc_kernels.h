@@ -44,7 +44,7 @@ size_t encode_state_bytes(uint64_t n_cells);
 // consecutive launches on the same scratch (each launch zeroes the other parity's accumulators).  Two launches.
 cudaError_t launch_encode(cudaStream_t st, const uint8_t* color, const uint8_t* glyph, uint32_t x, uint32_t y,
                           int mode, char* out, size_t cap, unsigned long long* total, void* scratch, size_t scratch_bytes,
-                          uint32_t parity);
+                          uint32_t parity, bool continues = false /* the cell stored before `color` precedes cell 0 */);
 
 // physics (rtc_shade.cu)
 cudaError_t launch_update_objects(cudaStream_t st, rtc_object* objs, int n, double dt);

@@ -165,3 +165,156 @@ class BandRenderer:
             if self.gl:
                 for p in self.peer_glyph:
                     self.ctx.ipc_close(p)
+
+
+class HostAssembledRenderer:
+    """Row bands with NO data-path collective: every rank traces its band (plus one context row above it), encodes
+    the band itself (rtc_encode_band) and copies its piece of the stream over ITS OWN PCIe link straight into one
+    frame buffer in shared, page-locked host memory, at the offset given by the stream lengths of the ranks before
+    it.  The frame is assembled where the reference's sink wants it -- in host memory (PrintMachine::
+    SetDataInBackBuffer) -- by 1/2/4/8 copy engines in parallel instead of one.
+
+      submit(params)  enqueue trace + shade + encode of this rank's band (two frames may be in flight)
+      collect()       oldest frame: publish this rank's stream length, wait for the lengths of the ranks before it,
+                      D2H the band stream into the shared frame; on rank 0 also wait for every rank and return
+                      (uint8 view of the frame, n_bytes), valid until the second submit after this call.
+    Cross-process state lives in the shared segment (lengths and frame tags); ranks poll it from the host.
+    """
+
+    HDR = 4096
+
+    def __init__(self, ctx, dist, rank, world, x, y, mode, name=None):
+        import ctypes
+        from multiprocessing import shared_memory
+        import numpy as np
+        import torch
+        from . import encode_capacity, mode_bpp, mode_has_glyph
+        self.torch, self.np, self.ctx, self.rank, self.world = torch, np, ctx, rank, world
+        self.x, self.y, self.W, self.mode = x, y, x - 1, mode
+        self.bpp, self.gl = mode_bpp(mode), bool(mode_has_glyph(mode))
+        self.bands = bands(y, world)
+        self.r0, self.r1 = self.bands[rank]
+        self.c0 = self.r0 - 1 if self.r0 > 0 else 0                     # first traced row (context)
+        rows_t = self.r1 - self.c0
+        W, bpp = self.W, self.bpp
+        u8 = dict(dtype=torch.uint8, device="cuda")
+        self.color = torch.empty(rows_t * W * bpp + 64, **u8)
+        self.glyph = torch.empty(rows_t * W + 64, **u8) if self.gl else None
+        self.band_cap = encode_capacity(x, max(1, self.r1 - self.r0), mode)
+        self.out = [torch.empty(self.band_cap, **u8) for _ in range(2)]
+        self.total = torch.zeros(2, dtype=torch.int64, device="cuda")
+        self.h_total = torch.zeros(2, dtype=torch.int64).pin_memory()
+        self.done_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        self.copy_stream = torch.cuda.Stream()
+        self.frame_cap = encode_capacity(x, y, mode)
+        size = self.HDR + 2 * self.frame_cap
+        names = [None]
+        if rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=size, name=name)
+            names = [self.shm.name]
+        if world > 1:
+            dist.broadcast_object_list(names, src=0)
+        if rank != 0:
+            self.shm = shared_memory.SharedMemory(name=names[0])
+        self._addr = ctypes.addressof(ctypes.c_char.from_buffer(self.shm.buf))
+        rc = torch.cuda.cudart().cudaHostRegister(self._addr, size, 1)       # portable; every rank pins its own mapping
+        if int(rc) != 0:
+            raise RuntimeError("cudaHostRegister failed: %s" % rc)
+        hdr = np.frombuffer(self.shm.buf, dtype=np.int64, count=self.HDR // 8)
+        if rank == 0:
+            hdr[:] = 0
+        # per slot: lens[world], len_tag[world], done_tag[world]; then consumed_tag[2]
+        self.lens = [hdr[(3 * s) * 16:(3 * s) * 16 + world] for s in range(2)]
+        self.len_tag = [hdr[(3 * s + 1) * 16:(3 * s + 1) * 16 + world] for s in range(2)]
+        self.done_tag = [hdr[(3 * s + 2) * 16:(3 * s + 2) * 16 + world] for s in range(2)]
+        self.consumed = hdr[96:98]
+        self.frames = [torch.frombuffer(self.shm.buf, dtype=torch.uint8, count=self.frame_cap,
+                                        offset=self.HDR + s * self.frame_cap) for s in range(2)]
+        if world > 1:
+            dist.barrier()                                                # header zeroed before anyone polls it
+        self.k_sub = 0
+        self.k_col = 0
+        self.k_step = 0
+        self.pending = []
+        self.t_wait_gpu = self.t_wait_len = self.t_copy = self.t_wait_done = 0.0
+
+    def step(self, params, flags=0, slot=None):
+        """Device work of one frame (what `value` times): trace + shade + encode of this rank's band."""
+        ctx, W, bpp = self.ctx, self.W, self.bpp
+        if slot is None:                           # free-running (device-timed loop): any slot will do
+            slot = self.k_step & 1
+            self.k_step += 1
+        rows = self.r1 - self.r0
+        ctx.trace_band(params, self.mode, self.c0, self.r1, self.color.data_ptr(), self.glyph.data_ptr() if self.gl else 0, flags)
+        skip = (self.r0 - self.c0) * W
+        ctx.encode_band(self.color.data_ptr() + skip * bpp, (self.glyph.data_ptr() + skip) if self.gl else 0, self.x, rows,
+                        self.mode, self.r0 > 0, self.out[slot].data_ptr(), self.band_cap, self.total[slot:].data_ptr())
+        return slot
+
+    def submit(self, params, flags=0):
+        import time
+        torch = self.torch
+        t0 = time.perf_counter()
+        slot = self.k_sub & 1                      # frame j of the submit/collect sequence lives in slot j & 1
+        self.k_sub += 1
+        self.step(params, flags, slot)
+        t1 = time.perf_counter()
+        self.h_total[slot:slot + 1].copy_(self.total[slot:slot + 1], non_blocking=True)
+        self.done_ev[slot].record(torch.cuda.current_stream())
+        self.pending.append(slot)                 # collect() takes frames in submission order, whatever step() did in between
+        self.t_submit_step = getattr(self, "t_submit_step", 0.0) + (t1 - t0)
+        self.t_submit_rest = getattr(self, "t_submit_rest", 0.0) + (time.perf_counter() - t1)
+        return slot
+
+    def _spin(self, cond):
+        import time
+        t0 = time.perf_counter()
+        while not cond():
+            if time.perf_counter() - t0 > 60.0:
+                raise RuntimeError("rank %d: timed out waiting for a peer in the shared frame header" % self.rank)
+
+    def collect(self):
+        torch = self.torch
+        k = self.k_col
+        self.k_col += 1
+        import time
+        slot, tag, g = self.pending.pop(0), k + 1, self.rank
+        t0 = time.perf_counter()
+        self.done_ev[slot].synchronize()
+        t1 = time.perf_counter()
+        n = int(self.h_total[slot])
+        self.lens[slot][g] = n
+        self.len_tag[slot][g] = tag
+        self._spin(lambda: all(self.len_tag[slot][h] >= tag for h in range(g)))
+        off = int(sum(int(self.lens[slot][h]) for h in range(g)))
+        # the frame two back used this slot: wait until rank 0 has released it
+        if k >= 2 and g != 0:
+            self._spin(lambda: self.consumed[slot] >= tag - 2)
+        t2 = time.perf_counter()
+        if n:
+            with torch.cuda.stream(self.copy_stream):
+                self.frames[slot][off:off + n].copy_(self.out[slot][:n], non_blocking=True)
+            self.copy_stream.synchronize()
+        t3 = time.perf_counter()
+        self.done_tag[slot][g] = tag
+        self.t_wait_gpu += t1 - t0; self.t_wait_len += t2 - t1; self.t_copy += t3 - t2
+        if g != 0:
+            return None, 0
+        self._spin(lambda: all(self.done_tag[slot][h] >= tag for h in range(self.world)))
+        self.t_wait_done += time.perf_counter() - t3
+        total = int(sum(int(self.lens[slot][h]) for h in range(self.world)))
+        self.consumed[slot ^ 1] = tag - 1        # the previous frame's buffer (other slot) may now be overwritten
+        return self.frames[slot][:total], total
+
+    def close(self):
+        try:
+            self.torch.cuda.cudart().cudaHostUnregister(self._addr)
+        except Exception:
+            pass
+        self.lens = self.len_tag = self.done_tag = self.consumed = self.frames = None
+        try:
+            self.shm.close()
+            if self.rank == 0:
+                self.shm.unlink()
+        except Exception:
+            pass

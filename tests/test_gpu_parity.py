@@ -333,3 +333,35 @@ def test_pipelined_submit_collect(ctx, rtc):
     with pytest.raises(rtc.RtcError, match="in flight"):
         ctx.submit(ps[2], RGB_PIXEL)
     ctx.collect(); ctx.collect()
+
+
+def test_band_encode_concatenates(ctx, rtc):
+    """Per-band encoding (multi-GPU without gathering planes): every band is traced with one context row above it and
+    encoded with rtc_encode_band(continues=1); the band streams concatenate to the whole frame's stream, bit for bit."""
+    import torch
+    objs = scenes.config_scene("config2_1080p_64")
+    x, y = 481, 270
+    p = rtc.camera_params(x, y, (0, 0, -120), (0, PI32, 0), 1.0 / (x - 1))
+    W = x - 1
+    ctx.set_objects(objs)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    for mode in (RGB_PIXEL, RGB_ASCII, BIT_ASCII, BIT_PIXEL):
+        ctx.render(p, mode)
+        want = ctx.frame_ansi()
+        bpp, gl = mode_bpp(mode), mode_has_glyph(mode)
+        pieces = []
+        for (r0, r1) in [(0, 67), (67, 135), (135, 136), (136, 136), (136, 270)]:       # ragged, 1-row and empty bands
+            c0 = r0 - 1 if r0 > 0 else 0                                              # context row
+            color = torch.zeros((r1 - c0) * W * bpp + 64, dtype=torch.uint8, device="cuda")
+            glyph = torch.zeros((r1 - c0) * W + 64, dtype=torch.uint8, device="cuda")
+            ctx.trace_band(p, mode, c0, r1, color.data_ptr(), glyph.data_ptr() if gl else 0)
+            skip = (r0 - c0) * W
+            cap = rtc.encode_capacity(x, max(1, r1 - r0), mode)
+            out = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+            total = torch.zeros(1, dtype=torch.int64, device="cuda")
+            ctx.encode_band(color.data_ptr() + skip * bpp, (glyph.data_ptr() + skip) if gl else 0, x, r1 - r0, mode,
+                            r0 > 0, out.data_ptr(), cap, total.data_ptr())
+            torch.cuda.synchronize()
+            pieces.append(out[:int(total.item())].cpu().numpy())
+        assert np.array_equal(np.concatenate(pieces), want), MODE_NAMES[mode]
+    ctx.set_stream(0)
