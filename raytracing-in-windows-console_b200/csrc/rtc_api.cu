@@ -244,29 +244,30 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
         CK(c->d_hit_t.ensure(n_px));
         CK(c->d_hit_idx.ensure(n_px));
         const rtc::FrameParams fp = make_frame(p, row0, row1);
-        const int n_chunks = n_slots == 0 ? 1 : (n_slots + rtc::kMaxSlotsPerLaunch - 1) / rtc::kMaxSlotsPerLaunch;
+        const rtc::TracePlan plan = rtc::plan_trace(p->x, row1 - row0, n_slots, c->sm_count);
+        const int n_chunks = n_slots == 0 ? 1 : (n_slots + plan.max_slots - 1) / plan.max_slots;
         if (n_chunks > 32) return fail(RTC_ERR_CAPACITY, "too many spheres (%d)", n_spheres);
         for (int ch = 0; ch < n_chunks; ++ch) {
-            const int s0 = ch * rtc::kMaxSlotsPerLaunch;
-            const int slots = n_slots - s0 < rtc::kMaxSlotsPerLaunch ? n_slots - s0 : rtc::kMaxSlotsPerLaunch;
+            const int s0 = ch * plan.max_slots;
+            const int slots = n_slots - s0 < plan.max_slots ? n_slots - s0 : plan.max_slots;
             const int sph = n_spheres - s0 < slots ? n_spheres - s0 : slots;
             const bool last = ch == n_chunks - 1;
             CK(rtc::launch_trace(c->stream, c->sm_count, fp, c->d_fast.p + 3 * (size_t)s0, c->d_exact.p + s0, c->d_sphere_obj.p + s0,
                                  sph, slots, c->d_objs.p, c->d_plane_obj.p, last ? n_planes : 0, c->d_hit_t.p,
-                                 c->d_hit_idx.p, c->d_counters.p + ch, ch > 0 ? 1 : 0, nullptr, nullptr));
+                                 c->d_hit_idx.p, c->d_counters.p + ch, ch > 0 ? 1 : 0, nullptr, nullptr, plan.threads));
             c->last_launches++;
         }
         if (shadows) {                                          // second pass: one ray per shaded pixel, cast from the light
             CK(c->d_shadow.ensure(n_px));
             for (int ch = 0; ch < n_chunks; ++ch) {
-                const int s0 = ch * rtc::kMaxSlotsPerLaunch;
-                const int slots = n_slots - s0 < rtc::kMaxSlotsPerLaunch ? n_slots - s0 : rtc::kMaxSlotsPerLaunch;
+                const int s0 = ch * plan.max_slots;
+                const int slots = n_slots - s0 < plan.max_slots ? n_slots - s0 : plan.max_slots;
                 const int sph = n_spheres - s0 < slots ? n_spheres - s0 : slots;
                 const bool last = ch == n_chunks - 1;
                 CK(rtc::launch_trace(c->stream, c->sm_count, fp, c->d_fast_l.p + 3 * (size_t)s0, c->d_exact_l.p + s0,
                                      c->d_sphere_obj.p + s0, sph, slots, c->d_objs.p, c->d_plane_obj.p, last ? n_planes : 0,
                                      c->d_hit_t.p, c->d_hit_idx.p, c->d_counters.p + 32 + ch, ch > 0 ? 1 : 0, rtc::kLightPos,
-                                     c->d_shadow.p));
+                                     c->d_shadow.p, plan.threads));
                 c->last_launches++;
             }
         }

@@ -9,19 +9,14 @@ namespace rtc {
 
 struct FrameParams;
 
-#ifndef RTC_TRACE_THREADS
-// Threads of the persistent ray-kernel CTA (one CTA per SM).  Measured on config 3 / config 4 (trace ms):
-// 512: 1.268 / 18.52, 640: 1.240 / 18.32, 768: 1.206 / 17.86, 896: 1.208 / 17.95, 1024: 1.208 / 18.23 (register cap
-// 64 -> spills; more sphere chunks) -- profiles/r01_trace_kernel_ncu.md.
-#define RTC_TRACE_THREADS 768
-#endif
-// sphere slots resident in shared memory per trace launch: 28 B per slot next to 192 B of ray state per thread
-constexpr int kMaxSlotsPerLaunch = ((227 * 1024 - RTC_TRACE_THREADS * 192) / 28) & ~3;
+// The persistent ray-kernel CTA (one per SM) exists with 24 and with 28 warps; plan_trace picks per launch.
+struct TracePlan { int threads; int max_slots; };   // threads per CTA; sphere slots resident in shared memory per launch
+TracePlan plan_trace(uint32_t x, uint32_t rows, int n_slots, int n_ctas);
 constexpr int kNumCounters = 64;           // per-frame device counters zeroed by the hoist kernel
 
 // kernel 0 / 1 (rtc_trace.cu)
 cudaError_t configure_trace();
-size_t trace_smem_bytes(int n_slots);
+size_t trace_smem_bytes(int n_slots, int threads);
 cudaError_t launch_hoist(cudaStream_t st, const rtc_object* objs, const int32_t* sphere_obj, int n_spheres,
                          int n_slots, const float cam[3], float* sph_fast, float4* sph_exact,
                          unsigned int* counters, int n_counters);
@@ -29,7 +24,7 @@ cudaError_t launch_trace(cudaStream_t st, int n_ctas, const FrameParams& fp, con
                          const int32_t* sphere_obj, int n_spheres, int n_slots, const rtc_object* objs,
                          const int32_t* plane_obj, int n_planes, float* hit_t, int32_t* hit_idx,
                          unsigned int* tile_counter, int carry_in, const float* light /* NULL: primary rays */,
-                         uint8_t* shadow);
+                         uint8_t* shadow, int threads);
 constexpr float kLightPos[3] = {1.0f, 50.0f, 0.0f};            // the reference's hard-coded light (RayTracing.cu:146)
 
 // kernel 2 (rtc_shade.cu)

@@ -7,9 +7,9 @@
 //   * All primary rays share the origin (RayTracing.cu:195), so oc = origin - centre and
 //     c = |oc|^2 - r^2 are per-sphere, per-frame constants: kernel 0 hoists them (bit-identical
 //     to what the reference recomputes per ray).
-//   * Kernel 1 is persistent: one 768-thread CTA per SM keeps the sphere list (up to 3032 spheres per
-//     launch; longer lists are chunked) in shared memory and walks 16x16-pixel screen tiles, one tile
-//     per warp, 8 rays per thread.
+//   * Kernel 1 is persistent: one CTA of 16..28 warps per SM (plan_trace picks the count from the number
+//     of tiles) keeps the sphere list (2156..4788 spheres per launch; longer lists are chunked) in shared
+//     memory and walks 16x16-pixel screen tiles, one tile per warp, 8 rays per thread.
 //   * The inner loop tests TWO spheres against one ray per packed instruction (FMUL2/FFMA2).
 //     Measured on B200: an FFMA2 only sustains 1 per 2 cycles when at most one operand pair is
 //     fresh (register-bank limit), and every ALU-pipe instruction (FMNMX3, FSETP, ...) costs
@@ -24,6 +24,8 @@
 //     decisions and distances are bit-identical to the reference.
 //   * The running best (distance, object index) per ray lives in shared memory: it is touched
 //     only on the (rare) exact path and would otherwise cost 16 registers in the hot loop.
+#include <cstdlib>
+
 #include "rtc_device.cuh"
 #include "rtc_kernels.h"
 
@@ -76,12 +78,12 @@ hoist_kernel(const rtc_object* __restrict__ objs, const int32_t* __restrict__ sp
 
 // ---- kernel 1: trace --------------------------------------------------------------------
 constexpr int kRays = 8;            // rays per thread
-constexpr int kThreads = RTC_TRACE_THREADS;   // 24 warps, one CTA per SM
+// Threads per CTA are a template parameter (compile-time state stride; a run-time stride cost 3 %): 768 (24 warps,
+// 80 registers) and 896 (28 warps, 72 registers) are instantiated and plan_trace picks per launch.
 constexpr int kTile = 16;           // warp tile = 16 x 16 pixels
-constexpr int kStateFloats = 6 * kRays * kThreads;   // best_t, best_idx, div2A, dir x/y/z
 
 // Shared-memory layout (dynamic): [exact float4 x n_slots][fast 12 B x n_slots][state]
-// state, each [kRays][kThreads]: best_t, best_idx, divTwoA, and the exact ray direction
+// state, each [kRays][blockDim.x]: best_t, best_idx, divTwoA, and the exact ray direction
 // (x, y, z) -- the rare exact path indexes rays dynamically, which registers cannot do.
 struct Smem {
     float4* exact;
@@ -93,13 +95,13 @@ struct Smem {
     float* diry;
     float* dirz;
 };
-__device__ __forceinline__ Smem carve(unsigned char* raw, int n_slots)
+__device__ __forceinline__ Smem carve(unsigned char* raw, int n_slots, int n_threads)
 {
     Smem s;
     s.exact = reinterpret_cast<float4*>(raw);
     s.fast = s.exact + n_slots;
     float* st = reinterpret_cast<float*>(s.fast + (n_slots >> 2) * 3);
-    constexpr int n = kRays * kThreads;
+    const int n = kRays * n_threads;
     s.best_t = st;
     s.best_idx = reinterpret_cast<int*>(st + n);
     s.div2A = st + 2 * n;
@@ -129,10 +131,11 @@ __device__ __forceinline__ float4 lds128(uint32_t addr)
 // order-independently as the lexicographic minimum of (distance, object index).
 // A cheap, rigorous lower bound of the hit distance skips candidates that cannot beat the
 // running best (most of them: a ray pierces ~N/100 spheres but only the nearest matters).
+template <int kThreads>
 __device__ __noinline__ void exact_group(const int32_t* __restrict__ sphere_obj, int n_slots, int g, uint32_t mask, int tid)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const Smem s = carve(smem_raw, n_slots);
+    const Smem s = carve(smem_raw, n_slots, kThreads);
     while (mask) {
         const int b = __ffs(mask) - 1;
         mask &= mask - 1;
@@ -171,7 +174,7 @@ __device__ __noinline__ void exact_group(const int32_t* __restrict__ sphere_obj,
 //   unchanged (the "camera" of this launch is the light).  A pixel is in shadow iff some object is hit at a distance
 //   strictly below |P' - light| -- the nearest-hit machinery with the running best initialised to that length and
 //   no object.  hit_t / hit_idx are INPUTS here; the output is one byte per pixel in `shadow`.
-template <bool SHADOW>
+template <bool SHADOW, int kThreads>
 __global__ void __launch_bounds__(kThreads, 1)
 trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float4* __restrict__ g_exact,
              const int32_t* __restrict__ sphere_obj, int n_spheres, int n_slots,
@@ -181,7 +184,7 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
              float lx, float ly, float lz, uint8_t* __restrict__ shadow)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const Smem s = carve(smem_raw, n_slots);
+    const Smem s = carve(smem_raw, n_slots, kThreads);
     const int tid = threadIdx.x, lane = tid & 31;
 
     // Stage the hoisted sphere list once per CTA (persistent kernel).
@@ -303,7 +306,7 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
                         mask |= not_finite(hi) ? (1u << (q * 16 + r * 2 + 1)) : 0u;
                     }
                 }
-                if (mask) exact_group(sphere_obj, n_slots, g, mask, tid);
+                if (mask) exact_group<kThreads>(sphere_obj, n_slots, g, mask, tid);
             }
         }
 
@@ -345,14 +348,43 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
 
 cudaError_t configure_trace()   // per device, once per context
 {
-    cudaError_t e = cudaFuncSetAttribute(trace_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(trace_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(trace_kernel<false, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(trace_kernel<true, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(trace_kernel<false, 896>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(trace_kernel<true, 896>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
-size_t trace_smem_bytes(int n_slots)
+size_t trace_smem_bytes(int n_slots, int threads)
 {
-    return (size_t)n_slots * 28 + (size_t)kStateFloats * 4;
+    return (size_t)n_slots * 28 + (size_t)threads * (6 * kRays * 4);   // spheres + best_t, best_idx, div2A, dir x/y/z
+}
+
+// Threads per CTA and sphere slots per launch for a band of `rows` rows.
+// A warp's work quantum is one 256-ray tile, so T tiles take ceil(T / (CTAs * warps)) tile times, and a tile time is
+// warps / throughput(warps).  With many waves 24 and 28 warps are equally fast (config 3: 1.2056 / 1.2078 ms; 16
+// warps: 1.2677), but an 8-GPU band of a 4K frame is 4080 tiles = 27.6 per SM: 28 warps finish it in ONE wave
+// (0.198 ms against 0.259 with 24, 0.230 with 16 -- profiles/r01_trace_kernel_ncu.md).  More warps leave less
+// shared memory for spheres, i.e. more launches over a long sphere list -- priced in per chunk.
+TracePlan plan_trace(uint32_t x, uint32_t rows, int n_slots, int n_ctas)
+{
+    static const char* force = getenv("RTC_TRACE_THREADS_FORCE");      // experiments only
+    const long long W = (long long)x - 1;
+    const long long tiles = ((W + kTile - 1) / kTile) * (((long long)rows + kTile - 1) / kTile);
+    TracePlan best{896, 0};
+    double best_cost = -1.0;
+    for (int w = 28; w >= 24; w -= 4) {                                // ties go to 28 warps
+        if (force && atoi(force) != w * 32) continue;
+        const int max_slots = (int)((227 * 1024 - (long long)w * 32 * (6 * kRays * 4)) / 28) & ~3;
+        const int chunks = n_slots <= max_slots ? 1 : (n_slots + max_slots - 1) / max_slots;
+        const long long per_wave = (long long)n_ctas * w;
+        const double waves = (double)((tiles + per_wave - 1) / per_wave);
+        // per chunk: the sphere loop over its share of the list + a fixed ray set-up / write-back worth ~40 sphere tests
+        const double cost = waves * w * ((double)(n_slots > 0 ? n_slots : 1) + 40.0 * chunks);
+        if (best_cost < 0.0 || cost < best_cost) { best_cost = cost; best.threads = w * 32; best.max_slots = max_slots; }
+    }
+    if (best.max_slots == 0) best.max_slots = (int)((227 * 1024 - (long long)best.threads * (6 * kRays * 4)) / 28) & ~3;
+    return best;
 }
 
 cudaError_t launch_hoist(cudaStream_t st, const rtc_object* objs, const int32_t* sphere_obj, int n_spheres,
@@ -369,16 +401,17 @@ cudaError_t launch_hoist(cudaStream_t st, const rtc_object* objs, const int32_t*
 cudaError_t launch_trace(cudaStream_t st, int n_ctas, const FrameParams& fp, const float* g_fast, const float4* g_exact,
                          const int32_t* sphere_obj, int n_spheres, int n_slots, const rtc_object* objs,
                          const int32_t* plane_obj, int n_planes, float* hit_t, int32_t* hit_idx,
-                         unsigned int* tile_counter, int carry_in, const float* light, uint8_t* shadow)
+                         unsigned int* tile_counter, int carry_in, const float* light, uint8_t* shadow, int threads)
 {
-    if (light)
-        trace_kernel<true><<<n_ctas, kThreads, trace_smem_bytes(n_slots), st>>>(
-            fp, g_fast, g_exact, sphere_obj, n_spheres, n_slots, objs, plane_obj, n_planes, hit_t, hit_idx, tile_counter,
-            carry_in, light[0], light[1], light[2], shadow);
-    else
-        trace_kernel<false><<<n_ctas, kThreads, trace_smem_bytes(n_slots), st>>>(
-            fp, g_fast, g_exact, sphere_obj, n_spheres, n_slots, objs, plane_obj, n_planes, hit_t, hit_idx, tile_counter,
-            carry_in, 0.f, 0.f, 0.f, nullptr);
+    const size_t smem = trace_smem_bytes(n_slots, threads);
+    const float l0 = light ? light[0] : 0.f, l1 = light ? light[1] : 0.f, l2 = light ? light[2] : 0.f;
+#define RTC_TRACE_LAUNCH(SH, T)                                                                                          \
+    trace_kernel<SH, T><<<n_ctas, T, smem, st>>>(fp, g_fast, g_exact, sphere_obj, n_spheres, n_slots, objs, plane_obj,  \
+                                                 n_planes, hit_t, hit_idx, tile_counter, carry_in, l0, l1, l2, shadow)
+    if (threads == 896) { if (light) RTC_TRACE_LAUNCH(true, 896); else RTC_TRACE_LAUNCH(false, 896); }
+    else if (threads == 768) { if (light) RTC_TRACE_LAUNCH(true, 768); else RTC_TRACE_LAUNCH(false, 768); }
+    else return cudaErrorInvalidValue;
+#undef RTC_TRACE_LAUNCH
     return cudaGetLastError();
 }
 
