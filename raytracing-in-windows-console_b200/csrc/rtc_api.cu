@@ -100,6 +100,7 @@ struct rtc_ctx {
     struct ViewI { int32_t* p = nullptr; } d_sphere_obj, d_plane_obj;
     DevBuf<float> d_fast;      // 12 B per sphere slot (slots padded to a multiple of 4)
     DevBuf<float4> d_exact;
+    DevBuf<float> d_dmin, d_dmin_l;   // per group of 4 spheres: lower bound of any hit distance (camera / light origin)
     DevBuf<float> d_fast_l;    // the same hoist with the light as origin (shadow-ray extension)
     DevBuf<float4> d_exact_l;
     DevBuf<uint8_t> d_shadow;  // 1 byte per pixel: occluded
@@ -151,6 +152,7 @@ int upload_scene(rtc_ctx* c)
     const size_t n_slots = (c->sphere_obj.size() + 3) & ~(size_t)3;
     CK(c->d_fast.ensure(n_slots > 0 ? 3 * n_slots : 12));
     CK(c->d_exact.ensure(n_slots > 0 ? n_slots : 4));
+    CK(c->d_dmin.ensure(n_slots > 0 ? n_slots / 4 + 4 : 4));
     // Stage in pinned memory (two slots: the previous upload may still be in flight), then ONE async copy.
     const size_t b_objs = (n * sizeof(rtc_object) + 63) & ~(size_t)63, b_sph = (n_slots * sizeof(int32_t) + 63) & ~(size_t)63,
                  b_pl = (c->plane_obj.size() * sizeof(int32_t) + 63) & ~(size_t)63;
@@ -229,14 +231,15 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
     c->last_launches = 0;
     if (record_events) CK(cudaEventRecord(c->ev[0], c->stream));
     CK(rtc::launch_hoist(c->stream, c->d_objs.p, c->d_sphere_obj.p, n_spheres, n_slots, p->cam_pos, c->d_fast.p,
-                         c->d_exact.p, c->d_counters.p, rtc::kNumCounters));
+                         c->d_exact.p, c->d_dmin.p, c->d_counters.p, rtc::kNumCounters));
     c->last_launches++;
     const bool shadows = (flags & RTC_FLAG_SHADOWS) != 0 && mode != RTC_SDL && mode != RTC_RGB_NORMALS;
     if (shadows) {
         CK(c->d_fast_l.ensure(n_slots > 0 ? 3 * (size_t)n_slots : 12));
         CK(c->d_exact_l.ensure(n_slots > 0 ? n_slots : 4));
+        CK(c->d_dmin_l.ensure(n_slots > 0 ? n_slots / 4 + 4 : 4));
         CK(rtc::launch_hoist(c->stream, c->d_objs.p, c->d_sphere_obj.p, n_spheres, n_slots, rtc::kLightPos, c->d_fast_l.p,
-                             c->d_exact_l.p, c->d_counters.p, 0));
+                             c->d_exact_l.p, c->d_dmin_l.p, c->d_counters.p, 0));
         c->last_launches++;
     }
     if (record_events) CK(cudaEventRecord(c->ev[1], c->stream));
@@ -252,7 +255,8 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
             const int slots = n_slots - s0 < plan.max_slots ? n_slots - s0 : plan.max_slots;
             const int sph = n_spheres - s0 < slots ? n_spheres - s0 : slots;
             const bool last = ch == n_chunks - 1;
-            CK(rtc::launch_trace(c->stream, c->sm_count, fp, c->d_fast.p + 3 * (size_t)s0, c->d_exact.p + s0, c->d_sphere_obj.p + s0,
+            CK(rtc::launch_trace(c->stream, c->sm_count, fp, c->d_fast.p + 3 * (size_t)s0, c->d_exact.p + s0, c->d_dmin.p + s0 / 4,
+                                 c->d_sphere_obj.p + s0,
                                  sph, slots, c->d_objs.p, c->d_plane_obj.p, last ? n_planes : 0, c->d_hit_t.p,
                                  c->d_hit_idx.p, c->d_counters.p + ch, ch > 0 ? 1 : 0, nullptr, nullptr, plan.threads));
             c->last_launches++;
@@ -265,7 +269,7 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
                 const int sph = n_spheres - s0 < slots ? n_spheres - s0 : slots;
                 const bool last = ch == n_chunks - 1;
                 CK(rtc::launch_trace(c->stream, c->sm_count, fp, c->d_fast_l.p + 3 * (size_t)s0, c->d_exact_l.p + s0,
-                                     c->d_sphere_obj.p + s0, sph, slots, c->d_objs.p, c->d_plane_obj.p, last ? n_planes : 0,
+                                     c->d_dmin_l.p + s0 / 4, c->d_sphere_obj.p + s0, sph, slots, c->d_objs.p, c->d_plane_obj.p, last ? n_planes : 0,
                                      c->d_hit_t.p, c->d_hit_idx.p, c->d_counters.p + 32 + ch, ch > 0 ? 1 : 0, rtc::kLightPos,
                                      c->d_shadow.p, plan.threads));
                 c->last_launches++;
@@ -352,7 +356,7 @@ void rtc_destroy(rtc_ctx* c)
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     c->d_scene.release(); c->d_fast.release(); c->d_exact.release();
-    c->d_fast_l.release(); c->d_exact_l.release(); c->d_shadow.release();
+    c->d_fast_l.release(); c->d_exact_l.release(); c->d_shadow.release(); c->d_dmin.release(); c->d_dmin_l.release();
     c->d_hit_t.release(); c->d_hit_idx.release(); c->d_color.release(); c->d_glyph.release(); c->d_out[0].release(); c->d_out[1].release();
     c->d_desc.release(); c->d_counters.release(); c->d_total.release(); c->d_sink.release();
     c->h_total.release(); c->h_out[0].release(); c->h_out[1].release(); c->h_scene[0].release(); c->h_scene[1].release();

@@ -18,10 +18,10 @@ constexpr int kNumCounters = 64;           // per-frame device counters zeroed b
 cudaError_t configure_trace();
 size_t trace_smem_bytes(int n_slots, int threads);
 cudaError_t launch_hoist(cudaStream_t st, const rtc_object* objs, const int32_t* sphere_obj, int n_spheres,
-                         int n_slots, const float cam[3], float* sph_fast, float4* sph_exact,
+                         int n_slots, const float cam[3], float* sph_fast, float4* sph_exact, float* grp_dmin,
                          unsigned int* counters, int n_counters);
 cudaError_t launch_trace(cudaStream_t st, int n_ctas, const FrameParams& fp, const float* g_fast, const float4* g_exact,
-                         const int32_t* sphere_obj, int n_spheres, int n_slots, const rtc_object* objs,
+                         const float* g_dmin, const int32_t* sphere_obj, int n_spheres, int n_slots, const rtc_object* objs,
                          const int32_t* plane_obj, int n_planes, float* hit_t, int32_t* hit_idx,
                          unsigned int* tile_counter, int carry_in, const float* light /* NULL: primary rays */,
                          uint8_t* shadow, int threads);

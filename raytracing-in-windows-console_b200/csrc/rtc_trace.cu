@@ -48,12 +48,13 @@ namespace rtc {
 __global__ void __launch_bounds__(256)
 hoist_kernel(const rtc_object* __restrict__ objs, const int32_t* __restrict__ sphere_obj, int n_spheres,
              int n_slots, float camx, float camy, float camz, float* __restrict__ sph_fast,
-             float4* __restrict__ sph_exact, unsigned int* __restrict__ counters, int n_counters)
+             float4* __restrict__ sph_exact, float* __restrict__ grp_dmin, unsigned int* __restrict__ counters, int n_counters)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < n_counters) counters[j] = 0u;     // tile tickets for this frame
-    if (j >= n_slots) return;
+    // (no early return: the group minimum below is a warp shuffle; n_slots is a multiple of 4, blockDim of 32)
     float ocx = 0.f, ocy = 0.f, ocz = 0.f, c = 1.f, gx = 0.f, gy = 0.f, gz = 0.f;
+    float dmin = 3.0e38f;                     // lower bound of any reference hit distance on this sphere
     if (j < n_spheres) {
         const rtc_object& s = objs[sphere_obj[j]];
         ocx = sub(camx, s.center[0]);                                   // Sphere.cu:34
@@ -66,14 +67,24 @@ hoist_kernel(const rtc_object* __restrict__ objs, const int32_t* __restrict__ sp
         if (cd > 0.0f && cd < 3.0e38f) {
             const float g = RTC_TWO64 / sqrtf(cd);
             gx = ocx * g; gy = ocy * g; gz = ocz * g;
+            // A unit-direction ray from outside meets the sphere no nearer than |oc| - r; the reference's rounded
+            // distance (direction normalised to a few ulp, cancellation in -b - sqrt(disc) of order ulp(|oc|)) stays above
+            // that minus 1e-5 (|oc| + r) with a wide margin (DESIGN.md "reject bound").
+            const float len = sqrtf(oc2), r = fabsf(s.radius);
+            dmin = fmaxf((len - r) - 1.0e-5f * (len + r), 0.0f);
         } else {
             gx = gy = gz = inf;
+            dmin = 0.0f;
         }
     }
+    dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, 1));
+    dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, 2));
+    if (j >= n_slots) return;
     float* base = sph_fast + 12 * (j >> 2);
     const int k = j & 3;
     base[k] = gx; base[4 + k] = gy; base[8 + k] = gz;
     sph_exact[j] = make_float4(ocx, ocy, ocz, c);
+    if (k == 0) grp_dmin[j >> 2] = dmin;
 }
 
 // ---- kernel 1: trace --------------------------------------------------------------------
@@ -82,12 +93,13 @@ constexpr int kRays = 8;            // rays per thread
 // 80 registers) and 896 (28 warps, 72 registers) are instantiated and plan_trace picks per launch.
 constexpr int kTile = 16;           // warp tile = 16 x 16 pixels
 
-// Shared-memory layout (dynamic): [exact float4 x n_slots][fast 12 B x n_slots][state]
+// Shared-memory layout (dynamic): [exact float4 x n_slots][fast 12 B x n_slots][group dmin 4 B x n_slots/4][state]
 // state, each [kRays][blockDim.x]: best_t, best_idx, divTwoA, and the exact ray direction
 // (x, y, z) -- the rare exact path indexes rays dynamically, which registers cannot do.
 struct Smem {
     float4* exact;
     float4* fast;      // 3 float4 per group of 4 spheres
+    float* gdmin;      // per group of 4 spheres: lower bound of any hit distance
     float* best_t;
     int* best_idx;
     float* div2A;
@@ -100,7 +112,8 @@ __device__ __forceinline__ Smem carve(unsigned char* raw, int n_slots, int n_thr
     Smem s;
     s.exact = reinterpret_cast<float4*>(raw);
     s.fast = s.exact + n_slots;
-    float* st = reinterpret_cast<float*>(s.fast + (n_slots >> 2) * 3);
+    s.gdmin = reinterpret_cast<float*>(s.fast + (n_slots >> 2) * 3);
+    float* st = s.gdmin + (((n_slots >> 2) + 3) & ~3);
     const int n = kRays * n_threads;
     s.best_t = st;
     s.best_idx = reinterpret_cast<int*>(st + n);
@@ -177,7 +190,7 @@ __device__ __noinline__ void exact_group(const int32_t* __restrict__ sphere_obj,
 template <bool SHADOW, int kThreads>
 __global__ void __launch_bounds__(kThreads, 1)
 trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float4* __restrict__ g_exact,
-             const int32_t* __restrict__ sphere_obj, int n_spheres, int n_slots,
+             const float* __restrict__ g_dmin, const int32_t* __restrict__ sphere_obj, int n_spheres, int n_slots,
              const rtc_object* __restrict__ objs, const int32_t* __restrict__ plane_obj, int n_planes,
              float* __restrict__ hit_t, int32_t* __restrict__ hit_idx, unsigned int* __restrict__ tile_counter,
              int carry_in /* 1: continue from hit_t/hit_idx (sphere list chunking) */,
@@ -190,6 +203,7 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
     // Stage the hoisted sphere list once per CTA (persistent kernel).
     for (int i = tid; i < n_slots; i += kThreads) s.exact[i] = g_exact[i];
     for (int i = tid; i < (n_slots >> 2) * 3; i += kThreads) s.fast[i] = reinterpret_cast<const float4*>(g_fast)[i];
+    for (int i = tid; i < (n_slots >> 2); i += kThreads) s.gdmin[i] = g_dmin[i];
     __syncthreads();
 
     const uint32_t W = fp.x - 1u;
@@ -306,7 +320,15 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
                         mask |= not_finite(hi) ? (1u << (q * 16 + r * 2 + 1)) : 0u;
                     }
                 }
-                if (mask) exact_group<kThreads>(sphere_obj, n_slots, g, mask, tid);
+                if (mask) {
+                    // Rays whose running best is already nearer than anything in this group of 4 spheres can offer
+                    // drop out here (most candidates of a ray lie behind its nearest hit).
+                    const float gd = s.gdmin[g];
+#pragma unroll
+                    for (int r = 0; r < kRays; ++r)
+                        if (gd > s.best_t[r * kThreads + tid]) mask &= ~(0x00030003u << (2 * r));
+                    if (mask) exact_group<kThreads>(sphere_obj, n_slots, g, mask, tid);
+                }
             }
         }
 
@@ -357,7 +379,8 @@ cudaError_t configure_trace()   // per device, once per context
 
 size_t trace_smem_bytes(int n_slots, int threads)
 {
-    return (size_t)n_slots * 28 + (size_t)threads * (6 * kRays * 4);   // spheres + best_t, best_idx, div2A, dir x/y/z
+    return (size_t)n_slots * 28 + (size_t)(((n_slots >> 2) + 3) & ~3) * 4 +      // spheres, group bounds,
+           (size_t)threads * (6 * kRays * 4);                                     // best_t, best_idx, div2A, dir x/y/z
 }
 
 // Threads per CTA and sphere slots per launch for a band of `rows` rows.
@@ -375,7 +398,7 @@ TracePlan plan_trace(uint32_t x, uint32_t rows, int n_slots, int n_ctas)
     double best_cost = -1.0;
     for (int w = 28; w >= 24; w -= 4) {                                // ties go to 28 warps
         if (force && atoi(force) != w * 32) continue;
-        const int max_slots = (int)((227 * 1024 - (long long)w * 32 * (6 * kRays * 4)) / 28) & ~3;
+        const int max_slots = (int)((227 * 1024 - 16 - (long long)w * 32 * (6 * kRays * 4)) / 29) & ~3;
         const int chunks = n_slots <= max_slots ? 1 : (n_slots + max_slots - 1) / max_slots;
         const long long per_wave = (long long)n_ctas * w;
         const double waves = (double)((tiles + per_wave - 1) / per_wave);
@@ -383,30 +406,30 @@ TracePlan plan_trace(uint32_t x, uint32_t rows, int n_slots, int n_ctas)
         const double cost = waves * w * ((double)(n_slots > 0 ? n_slots : 1) + 40.0 * chunks);
         if (best_cost < 0.0 || cost < best_cost) { best_cost = cost; best.threads = w * 32; best.max_slots = max_slots; }
     }
-    if (best.max_slots == 0) best.max_slots = (int)((227 * 1024 - (long long)best.threads * (6 * kRays * 4)) / 28) & ~3;
+    if (best.max_slots == 0) best.max_slots = (int)((227 * 1024 - 16 - (long long)best.threads * (6 * kRays * 4)) / 29) & ~3;
     return best;
 }
 
 cudaError_t launch_hoist(cudaStream_t st, const rtc_object* objs, const int32_t* sphere_obj, int n_spheres,
-                         int n_slots, const float cam[3], float* sph_fast, float4* sph_exact,
+                         int n_slots, const float cam[3], float* sph_fast, float4* sph_exact, float* grp_dmin,
                          unsigned int* counters, int n_counters)
 {
     const int n = n_slots > n_counters ? n_slots : n_counters;
     if (n <= 0) return cudaSuccess;
     hoist_kernel<<<(n + 255) / 256, 256, 0, st>>>(objs, sphere_obj, n_spheres, n_slots, cam[0], cam[1], cam[2],
-                                                  sph_fast, sph_exact, counters, n_counters);
+                                                  sph_fast, sph_exact, grp_dmin, counters, n_counters);
     return cudaGetLastError();
 }
 
 cudaError_t launch_trace(cudaStream_t st, int n_ctas, const FrameParams& fp, const float* g_fast, const float4* g_exact,
-                         const int32_t* sphere_obj, int n_spheres, int n_slots, const rtc_object* objs,
+                         const float* g_dmin, const int32_t* sphere_obj, int n_spheres, int n_slots, const rtc_object* objs,
                          const int32_t* plane_obj, int n_planes, float* hit_t, int32_t* hit_idx,
                          unsigned int* tile_counter, int carry_in, const float* light, uint8_t* shadow, int threads)
 {
     const size_t smem = trace_smem_bytes(n_slots, threads);
     const float l0 = light ? light[0] : 0.f, l1 = light ? light[1] : 0.f, l2 = light ? light[2] : 0.f;
 #define RTC_TRACE_LAUNCH(SH, T)                                                                                          \
-    trace_kernel<SH, T><<<n_ctas, T, smem, st>>>(fp, g_fast, g_exact, sphere_obj, n_spheres, n_slots, objs, plane_obj,  \
+    trace_kernel<SH, T><<<n_ctas, T, smem, st>>>(fp, g_fast, g_exact, g_dmin, sphere_obj, n_spheres, n_slots, objs, plane_obj, \
                                                  n_planes, hit_t, hit_idx, tile_counter, carry_in, l0, l1, l2, shadow)
     if (threads == 896) { if (light) RTC_TRACE_LAUNCH(true, 896); else RTC_TRACE_LAUNCH(false, 896); }
     else if (threads == 768) { if (light) RTC_TRACE_LAUNCH(true, 768); else RTC_TRACE_LAUNCH(false, 768); }
