@@ -41,6 +41,7 @@ def parse_args():
                     help="N > 1: host = every rank encodes its band and copies its piece of the stream into one shared pinned "
                          "host frame (no data-path collective); ipc / nccl = planes gathered to GPU 0 over NVLink, encoded there")
     ap.add_argument("--orbit", type=int, default=0, help="camera orbit of this many frames (config 4: 120); 0 = fixed camera")
+    ap.add_argument("--cull", action="store_true", help="per-tile sphere culling on (identical results, fewer tests executed)")
     ap.add_argument("--shadows", action="store_true", help="shadow-ray extension on (second, light-origin trace pass)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -261,7 +262,7 @@ def run_ours(args):
     # --orbit N: frame i is seen from camera i mod N of an N-frame orbit about the scene centre
     cams = [scenes.config_camera(name, frame=k, n_frames=args.orbit) for k in range(args.orbit)] if args.orbit > 0 else [p]
     frame_no = [0]
-    rflags = rtc_b200.FLAG_SHADOWS if args.shadows else 0
+    rflags = (rtc_b200.FLAG_SHADOWS if args.shadows else 0) | (rtc_b200.FLAG_CULL if args.cull else 0)
 
     def next_cam():
         c = cams[frame_no[0] % len(cams)]
@@ -462,7 +463,7 @@ def run_ours(args):
         "config": {"workload": name, "x": x, "y": y, "rays_per_frame": frame_rays, "spheres": n_spheres,
                    "objects": int(len(objs)), "mode": args.mode, "parallelism": "rowband%d" % world,
                    "gather": args.gather if world > 1 else None,
-                   "bands": renderer.bands if renderer is not None else [[0, y]], "camera_orbit_frames": args.orbit, "shadow_rays": bool(args.shadows),
+                   "bands": renderer.bands if renderer is not None else [[0, y]], "camera_orbit_frames": args.orbit, "shadow_rays": bool(args.shadows), "sphere_culling": bool(args.cull),
                    "l2": "flushed between timed steps (256 MiB memset, untimed)"},
         "frames_per_s": 1e3 / ms_per_step,
         "clocks": clocks, "e2e": e2e,
@@ -471,7 +472,9 @@ def run_ours(args):
         trace_ms = stage["trace_ms"] / args.steps
         enc_ms = stage["encode_ms"] / args.steps
         n_passes = 2 if args.shadows else 1                    # the shadow pass runs the same packed test over every tile with a shaded pixel
-        achieved = 7.0 * frame_rays * n_spheres * n_passes / (trace_ms * 1e-3) / 1e12
+        tests_executed = ctx.timings()["sphere_tests"]         # of the last frame (tile-granular: >= rays x spheres per pass)
+        # FLOPs of the tests actually executed: rays x spheres per pass without culling, fewer with --cull
+        achieved = 7.0 * (tests_executed if args.cull else frame_rays * n_spheres * n_passes) / (trace_ms * 1e-3) / 1e12
         try:
             measured_ffma = max(ctx.fp32_peak(0, 3000)[0] for _ in range(2))
             measured_ffma2 = max(ctx.fp32_peak(1, 3000)[0] for _ in range(2))
@@ -485,6 +488,7 @@ def run_ours(args):
                             "peak_source": "%d SMs x 128 lanes x 2 FLOP x %.0f MHz (%s sm_max_mhz); not in MEASURED_PEAKS.json, which has HBM and bf16 tensor only"
                                            % (sm_count, pk["sm_max_mhz"], pk["source"]),
                             "algorithmic_flops_per_launch": 7.0 * frame_rays * n_spheres, "launches_in_kernel_ms": n_passes, "kernel_ms": trace_ms,
+                            "sphere_tests_executed": tests_executed, "sphere_tests_brute_force": frame_rays * n_spheres * n_passes,
                             "measured_ffma_tflops": measured_ffma, "measured_ffma2_tflops": measured_ffma2,
                             "frac_of_measured_ffma": (achieved / measured_ffma) if measured_ffma else None}
         enc_bytes = bpp * frame_rays + n_stream
@@ -505,6 +509,36 @@ def run_ours(args):
                                              "achieved_gbs": enc_bytes / (enc_ms * 1e-3) / 1e9,
                                              "cells_per_ns": frame_rays / (enc_ms * 1e6)}
         line["stages_ms"] = {k: v / args.steps for k, v in stage.items()}
+        if not args.cull:
+            # The same frames with per-tile sphere culling (RTC_FLAG_CULL): identical output (tests/test_gpu_parity.py::
+            # test_culling_is_invisible), fewer ray-sphere tests executed -- reported beside the brute-force headline
+            # because it changes the FLOP accounting the roofline above is defined on.
+            try:
+                cflags = rflags | rtc_b200.FLAG_CULL
+                for _ in range(3):
+                    ctx.render(next_cam(), mode, cflags)
+                torch.cuda.synchronize()
+                k = max(10, min(args.steps, 50))
+                cms, cst = 0.0, {"trace_ms": 0.0, "shade_ms": 0.0, "encode_ms": 0.0}
+                for _ in range(k):
+                    flush.zero_()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(stream)
+                    ctx.render(next_cam(), mode, cflags)
+                    b.record(stream)
+                    torch.cuda.synchronize()
+                    cms += a.elapsed_time(b)
+                    t = ctx.timings()
+                    for kk in cst:
+                        cst[kk] += t[kk]
+                cms /= k
+                line["with_culling"] = {"value": frame_rays / (cms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": cms,
+                                        "frames_per_s": 1e3 / cms, "stages_ms": {kk: v / k for kk, v in cst.items()},
+                                        "sphere_tests_executed": t["sphere_tests"],
+                                        "fraction_of_brute_force_tests": t["sphere_tests"] / max(1, frame_rays * n_spheres * n_passes),
+                                        "output": "bit-identical to the brute-force frame"}
+            except Exception as e:
+                line["with_culling"] = {"error": repr(e)}
         line["gpu_launches"] = int(launches_per_step * args.steps)
         if not args.no_cpu_baseline:
             line["ref_cuda_sm100"] = ref_cuda_sample(name, mode)

@@ -76,7 +76,13 @@ enum {
     /* rtc_update_objects: mirror the reference's launch bug -- its UpdateObjects launch
      * uses block = count threads, which CUDA rejects when count > 1024, so no object moves
      * (RayTracingManager.cu:89-107).  Without this flag all objects are updated.        */
-    RTC_FLAG_UPDATE_REF_LAUNCH_LIMIT = 1u << 1
+    RTC_FLAG_UPDATE_REF_LAUNCH_LIMIT = 1u << 1,
+    /* Per-tile sphere culling (the reference's author planned a Culling kernel and never wrote it:
+     * RayTracingManager.cu:46-51, :100-117).  Spheres are grouped by 4 along a Morton curve; per 16x16-pixel warp
+     * tile, groups whose bounding cone misses the tile's ray cone are skipped.  Results are identical bit for bit;
+     * only the number of ray-sphere tests executed changes (rtc_timings.sphere_tests), which is why the FP32 roofline
+     * is quoted with this flag off.                                                                               */
+    RTC_FLAG_CULL = 1u << 2
 };
 
 /* == RayTracingCPUToGPUData (reference RayTracingManager.h:9-19) without the vptrs.
@@ -114,6 +120,8 @@ typedef struct rtc_timings {
     float encode_ms;  /* kernel 3: ANSI encode (scan + scatter)            */
     float total_ms;   /* first launch to last kernel end                   */
     uint32_t launches;/* kernels launched by the last rtc_render           */
+    uint32_t reserved_;
+    uint64_t sphere_tests; /* packed ray-sphere tests executed (rays x spheres without RTC_FLAG_CULL, tile-granular) */
 } rtc_timings;
 
 /* ---- context ------------------------------------------------------------------------ */

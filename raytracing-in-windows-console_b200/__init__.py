@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 from . import _types, scenes  # noqa: F401
-from ._types import (BIT_ASCII, BIT_PIXEL, FLAG_SHADOWS, FLAG_UPDATE_REF_LAUNCH_LIMIT, MODE_NAMES,  # noqa: F401
+from ._types import (BIT_ASCII, BIT_PIXEL, FLAG_CULL, FLAG_SHADOWS, FLAG_UPDATE_REF_LAUNCH_LIMIT, MODE_NAMES,  # noqa: F401
                      OBJECT_DTYPE, RGB_ASCII, RGB_NORMALS, RGB_PIXEL, SDL, RtcParams, RtcTimings,
                      mode_bpp, mode_cell, mode_has_glyph, obj_ptr)
 
@@ -225,7 +225,7 @@ class Context:
         t = RtcTimings()
         _check(self.L.rtc_last_timings(self._h, ctypes.byref(t)))
         return dict(prep_ms=t.prep_ms, trace_ms=t.trace_ms, shade_ms=t.shade_ms, encode_ms=t.encode_ms,
-                    total_ms=t.total_ms, launches=t.launches)
+                    total_ms=t.total_ms, launches=t.launches, sphere_tests=int(t.sphere_tests))
 
     # -- stage level, caller-owned device memory (raw pointers, e.g. torch tensors' data_ptr()) ---
     def trace_band(self, params, mode, row0, row1, dev_color, dev_glyph=0, flags=0):

@@ -30,6 +30,8 @@ class RtcTimings(ctypes.Structure):
         ("encode_ms", ctypes.c_float),
         ("total_ms", ctypes.c_float),
         ("launches", ctypes.c_uint32),
+        ("reserved_", ctypes.c_uint32),
+        ("sphere_tests", ctypes.c_uint64),
     ]
 
 
@@ -60,6 +62,7 @@ MODE_NAMES = ["BIT_ASCII", "BIT_PIXEL", "RGB_ASCII", "RGB_PIXEL", "RGB_NORMALS",
 
 FLAG_SHADOWS = 1
 FLAG_UPDATE_REF_LAUNCH_LIMIT = 2
+FLAG_CULL = 4
 
 
 def mode_bpp(mode):

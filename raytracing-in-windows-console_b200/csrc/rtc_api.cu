@@ -12,11 +12,13 @@
 // There is no CPU fallback anywhere in this file: without a CUDA device rtc_create fails.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "rtc_device.cuh"
@@ -101,6 +103,10 @@ struct rtc_ctx {
     DevBuf<float> d_fast;      // 12 B per sphere slot (slots padded to a multiple of 4)
     DevBuf<float4> d_exact;
     DevBuf<float> d_dmin, d_dmin_l;   // per group of 4 spheres: lower bound of any hit distance (camera / light origin)
+    DevBuf<float4> d_cone, d_cone_l;  // per group: bounding cone seen from the origin (axis, cos half-angle) ...
+    DevBuf<float> d_sin, d_sin_l;     // ... and the sine of its half-angle (RTC_FLAG_CULL)
+    bool last_cull = false;
+    uint64_t last_rays = 0, last_spheres = 0;
     DevBuf<float> d_fast_l;    // the same hoist with the light as origin (shadow-ray extension)
     DevBuf<float4> d_exact_l;
     DevBuf<uint8_t> d_shadow;  // 1 byte per pixel: occluded
@@ -139,6 +145,41 @@ struct rtc_ctx {
 
 namespace {
 
+// Sphere slots in Morton (Z-curve) order of their centres, so that the 4 spheres that share a packed group -- and a
+// bounding cone for per-tile culling -- are neighbours in space.  The order is irrelevant to the result (the accept
+// rule is the lexicographic minimum of (distance, object index)); it is camera-independent, hence done here on the
+// host when the scene changes rather than per frame.
+void morton_order(const std::vector<rtc_object>& objs, std::vector<int32_t>& sphere_obj)
+{
+    const size_t n = sphere_obj.size();
+    if (n < 8) return;
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (int32_t i : sphere_obj)
+        for (int a = 0; a < 3; ++a) {
+            const float v = objs[i].center[a];
+            if (v == v && fabsf(v) < 1.0e30f) { lo[a] = v < lo[a] ? v : lo[a]; hi[a] = v > hi[a] ? v : hi[a]; }
+        }
+    std::vector<std::pair<uint32_t, int32_t>> keyed(n);
+    for (size_t k = 0; k < n; ++k) {
+        uint32_t code = 0;
+        for (int a = 0; a < 3; ++a) {
+            const float v = objs[sphere_obj[k]].center[a];
+            const float span = hi[a] - lo[a];
+            uint32_t q = 0;
+            if (v == v && fabsf(v) < 1.0e30f && span > 0.0f) {
+                const float t = (v - lo[a]) / span * 1023.0f;
+                q = t <= 0.0f ? 0u : t >= 1023.0f ? 1023u : (uint32_t)t;
+            }
+            q = (q | (q << 16)) & 0x030000FFu; q = (q | (q << 8)) & 0x0300F00Fu;          // spread 10 bits to every third bit
+            q = (q | (q << 4)) & 0x030C30C3u;  q = (q | (q << 2)) & 0x09249249u;
+            code |= q << a;
+        }
+        keyed[k] = std::make_pair(code, sphere_obj[k]);
+    }
+    std::sort(keyed.begin(), keyed.end());                      // ties fall back to the object index: deterministic
+    for (size_t k = 0; k < n; ++k) sphere_obj[k] = keyed[k].second;
+}
+
 int upload_scene(rtc_ctx* c)
 {
     if (!c->scene_dirty) return RTC_OK;
@@ -149,8 +190,11 @@ int upload_scene(rtc_ctx* c)
         if (c->objs[i].type == RTC_OBJ_SPHERE) c->sphere_obj.push_back((int32_t)i);
         else if (c->objs[i].type == RTC_OBJ_PLANE) c->plane_obj.push_back((int32_t)i);
     }
+    morton_order(c->objs, c->sphere_obj);
     const size_t n_slots = (c->sphere_obj.size() + 3) & ~(size_t)3;
     CK(c->d_fast.ensure(n_slots > 0 ? 3 * n_slots : 12));
+    CK(c->d_cone.ensure(n_slots > 0 ? n_slots / 4 + 4 : 4));
+    CK(c->d_sin.ensure(n_slots > 0 ? n_slots / 4 + 4 : 4));
     CK(c->d_exact.ensure(n_slots > 0 ? n_slots : 4));
     CK(c->d_dmin.ensure(n_slots > 0 ? n_slots / 4 + 4 : 4));
     // Stage in pinned memory (two slots: the previous upload may still be in flight), then ONE async copy.
@@ -230,16 +274,21 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
     const int n_planes = (int)c->plane_obj.size();
     c->last_launches = 0;
     if (record_events) CK(cudaEventRecord(c->ev[0], c->stream));
+    const bool cull = (flags & RTC_FLAG_CULL) != 0;
+    unsigned long long* stats = reinterpret_cast<unsigned long long*>(c->d_counters.p + rtc::kStatsCounter);   // zeroed by the hoist
     CK(rtc::launch_hoist(c->stream, c->d_objs.p, c->d_sphere_obj.p, n_spheres, n_slots, p->cam_pos, c->d_fast.p,
-                         c->d_exact.p, c->d_dmin.p, c->d_counters.p, rtc::kNumCounters));
+                         c->d_exact.p, c->d_dmin.p, c->d_cone.p, c->d_sin.p, c->d_counters.p, rtc::kNumCounters));
+    c->last_cull = cull; c->last_rays = (uint64_t)n_px; c->last_spheres = (uint64_t)n_spheres;
     c->last_launches++;
     const bool shadows = (flags & RTC_FLAG_SHADOWS) != 0 && mode != RTC_SDL && mode != RTC_RGB_NORMALS;
     if (shadows) {
         CK(c->d_fast_l.ensure(n_slots > 0 ? 3 * (size_t)n_slots : 12));
         CK(c->d_exact_l.ensure(n_slots > 0 ? n_slots : 4));
         CK(c->d_dmin_l.ensure(n_slots > 0 ? n_slots / 4 + 4 : 4));
+        CK(c->d_cone_l.ensure(n_slots > 0 ? n_slots / 4 + 4 : 4));
+        CK(c->d_sin_l.ensure(n_slots > 0 ? n_slots / 4 + 4 : 4));
         CK(rtc::launch_hoist(c->stream, c->d_objs.p, c->d_sphere_obj.p, n_spheres, n_slots, rtc::kLightPos, c->d_fast_l.p,
-                             c->d_exact_l.p, c->d_dmin_l.p, c->d_counters.p, 0));
+                             c->d_exact_l.p, c->d_dmin_l.p, c->d_cone_l.p, c->d_sin_l.p, c->d_counters.p, 0));
         c->last_launches++;
     }
     if (record_events) CK(cudaEventRecord(c->ev[1], c->stream));
@@ -256,9 +305,9 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
             const int sph = n_spheres - s0 < slots ? n_spheres - s0 : slots;
             const bool last = ch == n_chunks - 1;
             CK(rtc::launch_trace(c->stream, c->sm_count, fp, c->d_fast.p + 3 * (size_t)s0, c->d_exact.p + s0, c->d_dmin.p + s0 / 4,
-                                 c->d_sphere_obj.p + s0,
+                                 c->d_cone.p + s0 / 4, c->d_sin.p + s0 / 4, c->d_sphere_obj.p + s0,
                                  sph, slots, c->d_objs.p, c->d_plane_obj.p, last ? n_planes : 0, c->d_hit_t.p,
-                                 c->d_hit_idx.p, c->d_counters.p + ch, ch > 0 ? 1 : 0, nullptr, nullptr, plan.threads));
+                                 c->d_hit_idx.p, c->d_counters.p + ch, ch > 0 ? 1 : 0, nullptr, nullptr, plan.threads, cull, stats));
             c->last_launches++;
         }
         if (shadows) {                                          // second pass: one ray per shaded pixel, cast from the light
@@ -269,9 +318,10 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
                 const int sph = n_spheres - s0 < slots ? n_spheres - s0 : slots;
                 const bool last = ch == n_chunks - 1;
                 CK(rtc::launch_trace(c->stream, c->sm_count, fp, c->d_fast_l.p + 3 * (size_t)s0, c->d_exact_l.p + s0,
-                                     c->d_dmin_l.p + s0 / 4, c->d_sphere_obj.p + s0, sph, slots, c->d_objs.p, c->d_plane_obj.p, last ? n_planes : 0,
+                                     c->d_dmin_l.p + s0 / 4, c->d_cone_l.p + s0 / 4, c->d_sin_l.p + s0 / 4, c->d_sphere_obj.p + s0, sph, slots,
+                                     c->d_objs.p, c->d_plane_obj.p, last ? n_planes : 0,
                                      c->d_hit_t.p, c->d_hit_idx.p, c->d_counters.p + 32 + ch, ch > 0 ? 1 : 0, rtc::kLightPos,
-                                     c->d_shadow.p, plan.threads));
+                                     c->d_shadow.p, plan.threads, cull, stats + 1));
                 c->last_launches++;
             }
         }
@@ -357,6 +407,7 @@ void rtc_destroy(rtc_ctx* c)
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     c->d_scene.release(); c->d_fast.release(); c->d_exact.release();
     c->d_fast_l.release(); c->d_exact_l.release(); c->d_shadow.release(); c->d_dmin.release(); c->d_dmin_l.release();
+    c->d_cone.release(); c->d_cone_l.release(); c->d_sin.release(); c->d_sin_l.release();
     c->d_hit_t.release(); c->d_hit_idx.release(); c->d_color.release(); c->d_glyph.release(); c->d_out[0].release(); c->d_out[1].release();
     c->d_desc.release(); c->d_counters.release(); c->d_total.release(); c->d_sink.release();
     c->h_total.release(); c->h_out[0].release(); c->h_out[1].release(); c->h_scene[0].release(); c->h_scene[1].release();
@@ -636,6 +687,11 @@ int rtc_last_timings(rtc_ctx* c, rtc_timings* out)
     CK(cudaEventElapsedTime(&out->encode_ms, c->ev[3], c->ev[4]));
     CK(cudaEventElapsedTime(&out->total_ms, c->ev[0], c->ev[4]));
     out->launches = c->last_launches;
+    // packed ray-sphere tests the last frame executed: warps x groups x (4 spheres x 256 rays), both passes
+    unsigned long long groups[2] = {0ull, 0ull};
+    CK(cudaMemcpyAsync(groups, c->d_counters.p + rtc::kStatsCounter, sizeof groups, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    out->sphere_tests = (groups[0] + groups[1]) * 4ull * 256ull;
     return RTC_OK;
 }
 

@@ -13,18 +13,19 @@ struct FrameParams;
 struct TracePlan { int threads; int max_slots; };   // threads per CTA; sphere slots resident in shared memory per launch
 TracePlan plan_trace(uint32_t x, uint32_t rows, int n_slots, int n_ctas);
 constexpr int kNumCounters = 64;           // per-frame device counters zeroed by the hoist kernel
+constexpr int kStatsCounter = 60;          // [60..63]: two 64-bit counts of sphere groups tested (primary, shadow pass)
 
 // kernel 0 / 1 (rtc_trace.cu)
 cudaError_t configure_trace();
 size_t trace_smem_bytes(int n_slots, int threads);
 cudaError_t launch_hoist(cudaStream_t st, const rtc_object* objs, const int32_t* sphere_obj, int n_spheres,
                          int n_slots, const float cam[3], float* sph_fast, float4* sph_exact, float* grp_dmin,
-                         unsigned int* counters, int n_counters);
+                         float4* grp_cone, float* grp_sin, unsigned int* counters, int n_counters);
 cudaError_t launch_trace(cudaStream_t st, int n_ctas, const FrameParams& fp, const float* g_fast, const float4* g_exact,
-                         const float* g_dmin, const int32_t* sphere_obj, int n_spheres, int n_slots, const rtc_object* objs,
-                         const int32_t* plane_obj, int n_planes, float* hit_t, int32_t* hit_idx,
-                         unsigned int* tile_counter, int carry_in, const float* light /* NULL: primary rays */,
-                         uint8_t* shadow, int threads);
+                         const float* g_dmin, const float4* g_cone, const float* g_sin, const int32_t* sphere_obj, int n_spheres,
+                         int n_slots, const rtc_object* objs, const int32_t* plane_obj, int n_planes, float* hit_t,
+                         int32_t* hit_idx, unsigned int* tile_counter, int carry_in, const float* light /* NULL: primary rays */,
+                         uint8_t* shadow, int threads, bool cull, unsigned long long* groups_tested);
 constexpr float kLightPos[3] = {1.0f, 50.0f, 0.0f};            // the reference's hard-coded light (RayTracing.cu:146)
 
 // kernel 2 (rtc_shade.cu)

@@ -48,15 +48,18 @@ namespace rtc {
 __global__ void __launch_bounds__(256)
 hoist_kernel(const rtc_object* __restrict__ objs, const int32_t* __restrict__ sphere_obj, int n_spheres,
              int n_slots, float camx, float camy, float camz, float* __restrict__ sph_fast,
-             float4* __restrict__ sph_exact, float* __restrict__ grp_dmin, unsigned int* __restrict__ counters, int n_counters)
+             float4* __restrict__ sph_exact, float* __restrict__ grp_dmin, float4* __restrict__ grp_cone,
+             float* __restrict__ grp_sin, unsigned int* __restrict__ counters, int n_counters)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < n_counters) counters[j] = 0u;     // tile tickets for this frame
     // (no early return: the group minimum below is a warp shuffle; n_slots is a multiple of 4, blockDim of 32)
     float ocx = 0.f, ocy = 0.f, ocz = 0.f, c = 1.f, gx = 0.f, gy = 0.f, gz = 0.f;
     float dmin = 3.0e38f;                     // lower bound of any reference hit distance on this sphere
+    float wx = 0.f, wy = 0.f, wz = 0.f, wr = 0.f, wn = 0.f;   // world centre, radius, 1 if this slot holds a sphere
     if (j < n_spheres) {
         const rtc_object& s = objs[sphere_obj[j]];
+        wx = s.center[0]; wy = s.center[1]; wz = s.center[2]; wr = fabsf(s.radius); wn = 1.0f;
         ocx = sub(camx, s.center[0]);                                   // Sphere.cu:34
         ocy = sub(camy, s.center[1]);
         ocz = sub(camz, s.center[2]);
@@ -79,7 +82,40 @@ hoist_kernel(const rtc_object* __restrict__ objs, const int32_t* __restrict__ sp
     }
     dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, 1));
     dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, 2));
+    // Bounding sphere of the group of 4 (centre = mean of the centres, radius = max(|c_i - centre| + r_i)) as a cone
+    // seen from the ray origin: unit axis u, sin and cos of its half-angle, both rounded towards "wider".
+    // No sphere in the group: never kept.  Origin inside the bounding sphere or odd numbers: always kept.
+    float sx = wx, sy = wy, sz = wz, sn = wn;
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        sz += __shfl_xor_sync(0xffffffffu, sz, o); sn += __shfl_xor_sync(0xffffffffu, sn, o);
+    }
+    const float inv_n = sn > 0.0f ? 1.0f / sn : 0.0f;
+    const float mx = sx * inv_n, my = sy * inv_n, mz = sz * inv_n;
+    float R = wn > 0.0f ? sqrtf((wx - mx) * (wx - mx) + (wy - my) * (wy - my) + (wz - mz) * (wz - mz)) + wr : 0.0f;
+    R = fmaxf(R, __shfl_xor_sync(0xffffffffu, R, 1));
+    R = fmaxf(R, __shfl_xor_sync(0xffffffffu, R, 2));
     if (j >= n_slots) return;
+    if ((j & 3) == 0) {
+        float4 cone = make_float4(0.f, 0.f, 0.f, 3.0f);          // empty group: threshold 3 cos(theta) > 1 >= any dot
+        float sn_a = 0.0f;
+        if (sn > 0.0f) {
+            const float vx = mx - camx, vy = my - camy, vz = mz - camz;
+            const float L = sqrtf(vx * vx + vy * vy + vz * vz);
+            const float Ri = R * 1.00002f + 1.0e-5f * (L + R);   // inflated: covers the rounding of everything above
+            if (L > Ri && L < 3.0e37f && Ri == Ri) {
+                const float sa = fminf(Ri / L * 1.000001f + 1.0e-7f, 1.0f);
+                const float ca = sqrtf(fmaxf(1.0f - sa * sa, 0.0f)) * 0.999999f;
+                cone = make_float4(vx / L, vy / L, vz / L, ca);
+                sn_a = sa;
+            } else {
+                cone = make_float4(0.f, 0.f, 0.f, -3.0f);        // always kept: threshold < 0 <= dot = 0
+            }
+        }
+        grp_cone[j >> 2] = cone;
+        grp_sin[j >> 2] = sn_a;
+    }
     float* base = sph_fast + 12 * (j >> 2);
     const int k = j & 3;
     base[k] = gx; base[4 + k] = gy; base[8 + k] = gz;
@@ -100,6 +136,8 @@ struct Smem {
     float4* exact;
     float4* fast;      // 3 float4 per group of 4 spheres
     float* gdmin;      // per group of 4 spheres: lower bound of any hit distance
+    float4* gcone;     // per group: bounding cone seen from the ray origin (axis, cos half-angle) ...
+    float* gsin;       // ... and the sine of its half-angle
     float* best_t;
     int* best_idx;
     float* div2A;
@@ -112,8 +150,11 @@ __device__ __forceinline__ Smem carve(unsigned char* raw, int n_slots, int n_thr
     Smem s;
     s.exact = reinterpret_cast<float4*>(raw);
     s.fast = s.exact + n_slots;
-    s.gdmin = reinterpret_cast<float*>(s.fast + (n_slots >> 2) * 3);
-    float* st = s.gdmin + (((n_slots >> 2) + 3) & ~3);
+    const int ng4 = ((n_slots >> 2) + 3) & ~3;
+    s.gcone = s.fast + (n_slots >> 2) * 3;
+    s.gdmin = reinterpret_cast<float*>(s.gcone + ng4);
+    s.gsin = s.gdmin + ng4;
+    float* st = s.gsin + ng4;
     const int n = kRays * n_threads;
     s.best_t = st;
     s.best_idx = reinterpret_cast<int*>(st + n);
@@ -180,6 +221,60 @@ __device__ __noinline__ void exact_group(const int32_t* __restrict__ sphere_obj,
     }
 }
 
+// One group of 4 spheres (2 packed pairs) against the thread's 8 rays, operand-major: 64 packed ops (128 issue
+// cycles) + 3 LDS.128 + one NaN check; measured 4.37 cycles/test against the 4.0 of a pure FFMA2 stream
+// (profiles/r01_microbench.md).
+template <int kThreads>
+__device__ __forceinline__ void test_group(const Smem& s, uint32_t fa, int g, const float (&ex)[kRays], const float (&ey)[kRays],
+                                           const float (&ez)[kRays], const int32_t* __restrict__ sphere_obj, int n_slots, int tid)
+{
+    const f32x2 ZERO2 = pack2(0.0f, 0.0f);
+    const float4 FX = lds128(fa), FY = lds128(fa + 16u), FZ = lds128(fa + 32u);   // warp-broadcast
+    f32x2 u[2][kRays];
+    f32x2 acc0 = ZERO2, acc1 = ZERO2;                           // NaN-sticky "something overflowed"
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const f32x2 GX = q ? pack2(FX.z, FX.w) : pack2(FX.x, FX.y);
+        const f32x2 GY = q ? pack2(FY.z, FY.w) : pack2(FY.x, FY.y);
+        const f32x2 GZ = q ? pack2(FZ.z, FZ.w) : pack2(FZ.x, FZ.y);
+#pragma unroll
+        for (int r = 0; r < kRays; ++r) u[q][r] = mul2(pack2(ex[r], ex[r]), GX);             // FMUL2 x8, GX reused
+#pragma unroll
+        for (int r = 0; r < kRays; ++r) u[q][r] = fma2(pack2(ey[r], ey[r]), GY, u[q][r]);    // FFMA2 x8, GY reused
+#pragma unroll
+        for (int r = 0; r < kRays; ++r) u[q][r] = fma2(pack2(ez[r], ez[r]), GZ, u[q][r]);    // FFMA2 x8: +-inf <=> candidate
+#pragma unroll
+        for (int r = 0; r < kRays; ++r) {                                                     // FFMA2 x8: inf*0 -> NaN, sticky
+            if (r & 1) acc1 = fma2(u[q][r], ZERO2, acc1);
+            else acc0 = fma2(u[q][r], ZERO2, acc0);
+        }
+    }
+    float alo, ahi;
+    unpack2(add2(acc0, acc1), alo, ahi);
+    if (__any_sync(0xffffffffu, !(alo == ahi))) {                // NaN in either half (both are 0 otherwise)
+        uint32_t mask = 0;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+#pragma unroll
+            for (int r = 0; r < kRays; ++r) {
+                float lo, hi;
+                unpack2(u[q][r], lo, hi);
+                mask |= not_finite(lo) ? (1u << (q * 16 + r * 2)) : 0u;
+                mask |= not_finite(hi) ? (1u << (q * 16 + r * 2 + 1)) : 0u;
+            }
+        }
+        if (mask) {
+            // Rays whose running best is already nearer than anything in this group of 4 spheres can offer
+            // drop out here (most candidates of a ray lie behind its nearest hit).
+            const float gd = s.gdmin[g];
+#pragma unroll
+            for (int r = 0; r < kRays; ++r)
+                if (gd > s.best_t[r * kThreads + tid]) mask &= ~(0x00030003u << (2 * r));
+            if (mask) exact_group<kThreads>(sphere_obj, n_slots, g, mask, tid);
+        }
+    }
+}
+
 // SHADOW = false: primary rays from the camera (hit_t / hit_idx are the outputs).
 // SHADOW = true : the shadow-ray EXTENSION (the reference casts none).  One ray per shaded pixel, cast FROM
 //   THE LIGHT (1,50,0) toward the shaded point P' = P + n*1e-3: all shadow rays then share their origin exactly like
@@ -187,23 +282,29 @@ __device__ __noinline__ void exact_group(const int32_t* __restrict__ sphere_obj,
 //   unchanged (the "camera" of this launch is the light).  A pixel is in shadow iff some object is hit at a distance
 //   strictly below |P' - light| -- the nearest-hit machinery with the running best initialised to that length and
 //   no object.  hit_t / hit_idx are INPUTS here; the output is one byte per pixel in `shadow`.
-template <bool SHADOW, int kThreads>
+// CULL = true (RTC_FLAG_CULL): per warp tile, the groups of 4 spheres whose bounding cone (hoisted) misses the tile's
+//   ray cone are skipped -- results are identical, far fewer tests are executed (the count is reported).
+template <bool SHADOW, int kThreads, bool CULL>
 __global__ void __launch_bounds__(kThreads, 1)
 trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float4* __restrict__ g_exact,
-             const float* __restrict__ g_dmin, const int32_t* __restrict__ sphere_obj, int n_spheres, int n_slots,
+             const float* __restrict__ g_dmin, const float4* __restrict__ g_cone, const float* __restrict__ g_sin,
+             const int32_t* __restrict__ sphere_obj, int n_spheres, int n_slots,
              const rtc_object* __restrict__ objs, const int32_t* __restrict__ plane_obj, int n_planes,
              float* __restrict__ hit_t, int32_t* __restrict__ hit_idx, unsigned int* __restrict__ tile_counter,
              int carry_in /* 1: continue from hit_t/hit_idx (sphere list chunking) */,
-             float lx, float ly, float lz, uint8_t* __restrict__ shadow)
+             float lx, float ly, float lz, uint8_t* __restrict__ shadow, unsigned long long* __restrict__ groups_tested)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem s = carve(smem_raw, n_slots, kThreads);
     const int tid = threadIdx.x, lane = tid & 31;
+    unsigned int my_groups = 0;                                  // groups of 4 spheres this warp ran the packed test on
 
     // Stage the hoisted sphere list once per CTA (persistent kernel).
     for (int i = tid; i < n_slots; i += kThreads) s.exact[i] = g_exact[i];
     for (int i = tid; i < (n_slots >> 2) * 3; i += kThreads) s.fast[i] = reinterpret_cast<const float4*>(g_fast)[i];
     for (int i = tid; i < (n_slots >> 2); i += kThreads) s.gdmin[i] = g_dmin[i];
+    if (CULL)
+        for (int i = tid; i < (n_slots >> 2); i += kThreads) { s.gcone[i] = g_cone[i]; s.gsin[i] = g_sin[i]; }
     __syncthreads();
 
     const uint32_t W = fp.x - 1u;
@@ -214,7 +315,6 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
     const V3 cam = v3(fp.cam[0], fp.cam[1], fp.cam[2]);
     const V3 o = SHADOW ? v3(lx, ly, lz) : cam;                 // common origin of this launch's rays
     const uint32_t px = lane & 15u, py = lane >> 4;
-    const f32x2 ZERO2 = pack2(0.0f, 0.0f);
     const uint32_t fast_base = (uint32_t)__cvta_generic_to_shared(s.fast);
 
     for (;;) {
@@ -280,54 +380,65 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
             }
         }
 
-        // ---- hot loop: 4 spheres (2 packed pairs) x 8 rays per iteration, operand-major ----------
-        // 64 packed ops (128 issue cycles) + 3 LDS.128 + one NaN check per iteration; measured
-        // 4.37 cycles/test against the 4.0 of a pure FFMA2 stream (profiles/r01_microbench.md).
-        uint32_t fa = fast_base;
+        // ---- hot loop over groups of 4 spheres ---------------------------------------------------------
+        if (!CULL) {
+            uint32_t fa = fast_base;
 #pragma unroll 2
-        for (int g = 0; g < n_groups; ++g, fa += 48u) {
-            const float4 FX = lds128(fa), FY = lds128(fa + 16u), FZ = lds128(fa + 32u);   // warp-broadcast
-            f32x2 u[2][kRays];
-            f32x2 acc0 = ZERO2, acc1 = ZERO2;                           // NaN-sticky "something overflowed"
+            for (int g = 0; g < n_groups; ++g, fa += 48u) test_group<kThreads>(s, fa, g, ex, ey, ez, sphere_obj, n_slots, tid);
+            my_groups += (unsigned int)n_groups;
+        } else {
+            // Bounding cone of this warp's (active) rays: axis = normalised sum of the directions, cos(theta) = the
+            // smallest axis.direction, both widened by the rounding slack.  A group is kept iff the angle between the
+            // axes is at most theta + alpha: dot >= cos(theta) cos(alpha) - sin(theta) sin(alpha).  Wide cones
+            // (tiny consoles, scattered shadow rays) keep everything.
+            float ax = 0.f, ay = 0.f, az = 0.f;
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const f32x2 GX = q ? pack2(FX.z, FX.w) : pack2(FX.x, FX.y);
-                const f32x2 GY = q ? pack2(FY.z, FY.w) : pack2(FY.x, FY.y);
-                const f32x2 GZ = q ? pack2(FZ.z, FZ.w) : pack2(FZ.x, FZ.y);
-#pragma unroll
-                for (int r = 0; r < kRays; ++r) u[q][r] = mul2(pack2(ex[r], ex[r]), GX);             // FMUL2 x8, GX reused
-#pragma unroll
-                for (int r = 0; r < kRays; ++r) u[q][r] = fma2(pack2(ey[r], ey[r]), GY, u[q][r]);    // FFMA2 x8, GY reused
-#pragma unroll
-                for (int r = 0; r < kRays; ++r) u[q][r] = fma2(pack2(ez[r], ez[r]), GZ, u[q][r]);    // FFMA2 x8: +-inf <=> candidate
-#pragma unroll
-                for (int r = 0; r < kRays; ++r) {                                                     // FFMA2 x8: inf*0 -> NaN, sticky
-                    if (r & 1) acc1 = fma2(u[q][r], ZERO2, acc1);
-                    else acc0 = fma2(u[q][r], ZERO2, acc0);
-                }
+            for (int r = 0; r < kRays; ++r) {
+                const int slot = r * kThreads + tid;
+                ax += s.dirx[slot]; ay += s.diry[slot]; az += s.dirz[slot];      // inactive shadow rays hold 0
             }
-            float alo, ahi;
-            unpack2(add2(acc0, acc1), alo, ahi);
-            if (__any_sync(0xffffffffu, !(alo == ahi))) {                // NaN in either half (both are 0 otherwise)
-                uint32_t mask = 0;
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
+            for (int o = 16; o > 0; o >>= 1) {
+                ax += __shfl_xor_sync(0xffffffffu, ax, o); ay += __shfl_xor_sync(0xffffffffu, ay, o);
+                az += __shfl_xor_sync(0xffffffffu, az, o);
+            }
+            const float al = sqrtf(ax * ax + ay * ay + az * az);
+            const bool axis_ok = al > 1.0e-3f && al < 1.0e30f;
+            const float il = axis_ok ? 1.0f / al : 0.0f;
+            ax *= il; ay *= il; az *= il;
+            float cmin = 1.0f;
 #pragma unroll
-                    for (int r = 0; r < kRays; ++r) {
-                        float lo, hi;
-                        unpack2(u[q][r], lo, hi);
-                        mask |= not_finite(lo) ? (1u << (q * 16 + r * 2)) : 0u;
-                        mask |= not_finite(hi) ? (1u << (q * 16 + r * 2 + 1)) : 0u;
-                    }
+            for (int r = 0; r < kRays; ++r) {
+                const int slot = r * kThreads + tid;
+                const float dx = s.dirx[slot], dy = s.diry[slot], dz = s.dirz[slot];
+                const float dd = ax * dx + ay * dy + az * dz;
+                const bool active = !SHADOW || s.best_t[slot] >= 0.0f;
+                cmin = fminf(cmin, active ? dd : 1.0f);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cmin = fminf(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
+            const float ct = cmin - 4.0e-6f;                                     // wider: unit vectors are unit to ~2e-7
+            const bool keep_all = !axis_ok || !(ct > 0.5f);
+            const float st = sqrtf(fmaxf(1.0f - ct * ct, 0.0f)) + 4.0e-6f;
+            for (int gb = 0; gb < n_groups; gb += 32) {
+                const int gi = gb + lane;
+                bool keep = false;
+                if (gi < n_groups) {
+                    const float4 cn = s.gcone[gi];
+                    const float thr = ct * cn.w - st * s.gsin[gi] - 4.0e-6f;
+                    keep = keep_all ? (cn.w < 2.0f) : (ax * cn.x + ay * cn.y + az * cn.z >= thr);
                 }
-                if (mask) {
-                    // Rays whose running best is already nearer than anything in this group of 4 spheres can offer
-                    // drop out here (most candidates of a ray lie behind its nearest hit).
-                    const float gd = s.gdmin[g];
-#pragma unroll
-                    for (int r = 0; r < kRays; ++r)
-                        if (gd > s.best_t[r * kThreads + tid]) mask &= ~(0x00030003u << (2 * r));
-                    if (mask) exact_group<kThreads>(sphere_obj, n_slots, g, mask, tid);
+                uint32_t m = __ballot_sync(0xffffffffu, keep);
+                my_groups += (unsigned int)__popc(m);
+                while (m) {
+                    const int g0 = gb + __ffs(m) - 1;
+                    m &= m - 1;
+                    test_group<kThreads>(s, fast_base + 48u * (uint32_t)g0, g0, ex, ey, ez, sphere_obj, n_slots, tid);
+                    if (m) {                                     // a second group back to back: the unroll-by-2 of the brute-force loop
+                        const int g1 = gb + __ffs(m) - 1;
+                        m &= m - 1;
+                        test_group<kThreads>(s, fast_base + 48u * (uint32_t)g1, g1, ex, ey, ez, sphere_obj, n_slots, tid);
+                    }
                 }
             }
         }
@@ -366,20 +477,23 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
             }
         }
     }
+    if (lane == 0 && groups_tested != nullptr && my_groups) atomicAdd(groups_tested, (unsigned long long)my_groups);
 }
 
 cudaError_t configure_trace()   // per device, once per context
 {
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(trace_kernel<false, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(trace_kernel<true, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(trace_kernel<false, 896>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
-    return cudaFuncSetAttribute(trace_kernel<true, 896>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+#define RTC_TRACE_ATTR(SH, T, C)                                                                                             \
+    if ((e = cudaFuncSetAttribute(trace_kernel<SH, T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e
+    RTC_TRACE_ATTR(false, 768, false); RTC_TRACE_ATTR(true, 768, false); RTC_TRACE_ATTR(false, 896, false); RTC_TRACE_ATTR(true, 896, false);
+    RTC_TRACE_ATTR(false, 768, true);  RTC_TRACE_ATTR(true, 768, true);  RTC_TRACE_ATTR(false, 896, true);  RTC_TRACE_ATTR(true, 896, true);
+#undef RTC_TRACE_ATTR
+    return cudaSuccess;
 }
 
 size_t trace_smem_bytes(int n_slots, int threads)
 {
-    return (size_t)n_slots * 28 + (size_t)(((n_slots >> 2) + 3) & ~3) * 4 +      // spheres, group bounds,
+    return (size_t)n_slots * 28 + (size_t)(((n_slots >> 2) + 3) & ~3) * 24 +     // spheres, per-group bounds (4 + 16 + 4 B),
            (size_t)threads * (6 * kRays * 4);                                     // best_t, best_idx, div2A, dir x/y/z
 }
 
@@ -398,7 +512,7 @@ TracePlan plan_trace(uint32_t x, uint32_t rows, int n_slots, int n_ctas)
     double best_cost = -1.0;
     for (int w = 28; w >= 24; w -= 4) {                                // ties go to 28 warps
         if (force && atoi(force) != w * 32) continue;
-        const int max_slots = (int)((227 * 1024 - 16 - (long long)w * 32 * (6 * kRays * 4)) / 29) & ~3;
+        const int max_slots = (int)((227 * 1024 - 96 - (long long)w * 32 * (6 * kRays * 4)) / 34) & ~3;
         const int chunks = n_slots <= max_slots ? 1 : (n_slots + max_slots - 1) / max_slots;
         const long long per_wave = (long long)n_ctas * w;
         const double waves = (double)((tiles + per_wave - 1) / per_wave);
@@ -406,34 +520,42 @@ TracePlan plan_trace(uint32_t x, uint32_t rows, int n_slots, int n_ctas)
         const double cost = waves * w * ((double)(n_slots > 0 ? n_slots : 1) + 40.0 * chunks);
         if (best_cost < 0.0 || cost < best_cost) { best_cost = cost; best.threads = w * 32; best.max_slots = max_slots; }
     }
-    if (best.max_slots == 0) best.max_slots = (int)((227 * 1024 - 16 - (long long)best.threads * (6 * kRays * 4)) / 29) & ~3;
+    if (best.max_slots == 0) best.max_slots = (int)((227 * 1024 - 96 - (long long)best.threads * (6 * kRays * 4)) / 34) & ~3;
     return best;
 }
 
 cudaError_t launch_hoist(cudaStream_t st, const rtc_object* objs, const int32_t* sphere_obj, int n_spheres,
                          int n_slots, const float cam[3], float* sph_fast, float4* sph_exact, float* grp_dmin,
-                         unsigned int* counters, int n_counters)
+                         float4* grp_cone, float* grp_sin, unsigned int* counters, int n_counters)
 {
     const int n = n_slots > n_counters ? n_slots : n_counters;
     if (n <= 0) return cudaSuccess;
     hoist_kernel<<<(n + 255) / 256, 256, 0, st>>>(objs, sphere_obj, n_spheres, n_slots, cam[0], cam[1], cam[2],
-                                                  sph_fast, sph_exact, grp_dmin, counters, n_counters);
+                                                  sph_fast, sph_exact, grp_dmin, grp_cone, grp_sin, counters, n_counters);
     return cudaGetLastError();
 }
 
 cudaError_t launch_trace(cudaStream_t st, int n_ctas, const FrameParams& fp, const float* g_fast, const float4* g_exact,
-                         const float* g_dmin, const int32_t* sphere_obj, int n_spheres, int n_slots, const rtc_object* objs,
-                         const int32_t* plane_obj, int n_planes, float* hit_t, int32_t* hit_idx,
-                         unsigned int* tile_counter, int carry_in, const float* light, uint8_t* shadow, int threads)
+                         const float* g_dmin, const float4* g_cone, const float* g_sin, const int32_t* sphere_obj, int n_spheres,
+                         int n_slots, const rtc_object* objs, const int32_t* plane_obj, int n_planes, float* hit_t,
+                         int32_t* hit_idx, unsigned int* tile_counter, int carry_in, const float* light, uint8_t* shadow,
+                         int threads, bool cull, unsigned long long* groups_tested)
 {
     const size_t smem = trace_smem_bytes(n_slots, threads);
     const float l0 = light ? light[0] : 0.f, l1 = light ? light[1] : 0.f, l2 = light ? light[2] : 0.f;
-#define RTC_TRACE_LAUNCH(SH, T)                                                                                          \
-    trace_kernel<SH, T><<<n_ctas, T, smem, st>>>(fp, g_fast, g_exact, g_dmin, sphere_obj, n_spheres, n_slots, objs, plane_obj, \
-                                                 n_planes, hit_t, hit_idx, tile_counter, carry_in, l0, l1, l2, shadow)
-    if (threads == 896) { if (light) RTC_TRACE_LAUNCH(true, 896); else RTC_TRACE_LAUNCH(false, 896); }
-    else if (threads == 768) { if (light) RTC_TRACE_LAUNCH(true, 768); else RTC_TRACE_LAUNCH(false, 768); }
+#define RTC_TRACE_LAUNCH(SH, T, C)                                                                                       \
+    trace_kernel<SH, T, C><<<n_ctas, T, smem, st>>>(fp, g_fast, g_exact, g_dmin, g_cone, g_sin, sphere_obj, n_spheres,  \
+                                                    n_slots, objs, plane_obj, n_planes, hit_t, hit_idx, tile_counter,   \
+                                                    carry_in, l0, l1, l2, shadow, groups_tested)
+#define RTC_TRACE_PICK(T)                                                                                                \
+    do {                                                                                                                 \
+        if (light) { if (cull) RTC_TRACE_LAUNCH(true, T, true); else RTC_TRACE_LAUNCH(true, T, false); }                 \
+        else       { if (cull) RTC_TRACE_LAUNCH(false, T, true); else RTC_TRACE_LAUNCH(false, T, false); }               \
+    } while (0)
+    if (threads == 896) RTC_TRACE_PICK(896);
+    else if (threads == 768) RTC_TRACE_PICK(768);
     else return cudaErrorInvalidValue;
+#undef RTC_TRACE_PICK
 #undef RTC_TRACE_LAUNCH
     return cudaGetLastError();
 }

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from rtc_b200 import scenes
-from rtc_b200._types import (BIT_ASCII, BIT_PIXEL, FLAG_SHADOWS, FLAG_UPDATE_REF_LAUNCH_LIMIT, MODE_NAMES,
+from rtc_b200._types import (BIT_ASCII, BIT_PIXEL, FLAG_CULL, FLAG_SHADOWS, FLAG_UPDATE_REF_LAUNCH_LIMIT, MODE_NAMES,
                              OBJECT_DTYPE, RGB_ASCII, RGB_NORMALS, RGB_PIXEL, SDL, mode_bpp, mode_cell, mode_has_glyph)
 from util import PI32, objs_from_bytes, params_from_bytes, parse_stream
 
@@ -365,3 +365,39 @@ def test_band_encode_concatenates(ctx, rtc):
             pieces.append(out[:int(total.item())].cpu().numpy())
         assert np.array_equal(np.concatenate(pieces), want), MODE_NAMES[mode]
     ctx.set_stream(0)
+
+
+def test_culling_is_invisible(ctx, oracle, rtc):
+    """RTC_FLAG_CULL (per-tile sphere-group culling) must not change a single hit record, colour or stream byte:
+    whole frames against the oracle with the flag on, primary and shadow passes, narrow and wide tile cones, chunked
+    sphere lists, camera inside the cloud; and it must actually skip work."""
+    objs = scenes.config_scene("config2_1080p_64")
+    p = scenes.config_camera("config2_1080p_64")
+    check_frame(ctx, oracle, objs, p, RGB_PIXEL, flags=FLAG_CULL)
+    check_frame(ctx, oracle, objs, p, RGB_ASCII, flags=FLAG_CULL | FLAG_SHADOWS)
+    # wide cones: tiny consoles take the keep-all path
+    small = rtc.camera_params(64, 20, (0, 0, 0), (0, PI32, 0))
+    check_frame(ctx, oracle, scenes.default_scene(), small, RGB_PIXEL, flags=FLAG_CULL)
+    check_frame(ctx, oracle, scenes.default_scene(), small, BIT_ASCII, flags=FLAG_CULL | FLAG_SHADOWS)
+    # many spheres: several shared-memory chunks, ragged last group, camera inside the cloud and inside a sphere
+    many = scenes.random_spheres(9001, 33)
+    q = rtc.camera_params(241, 120, (0, 0, -120), (0, PI32, 0), 1.0 / 240)
+    check_frame(ctx, oracle, many, q, RGB_PIXEL, flags=FLAG_CULL)
+    inside = rtc.camera_params(161, 90, (3, -2, 5), (0.3, 1.0, 0), 1.0 / 160)
+    check_frame(ctx, oracle, scenes.random_spheres(700, 34), inside, RGB_PIXEL, flags=FLAG_CULL)
+    check_frame(ctx, oracle, scenes.random_spheres(700, 34), inside, RGB_PIXEL, flags=FLAG_CULL | FLAG_SHADOWS)
+    # full-size config 3: bands against the oracle, whole frame against the brute-force GPU path, and the work saved
+    objs = scenes.config_scene("config3_4k_1024")
+    p = scenes.config_camera("config3_4k_1024")
+    n_px = (p.x - 1) * p.y
+    ctx.set_objects(objs)
+    ctx.render(p, RGB_PIXEL)
+    d0, i0 = ctx.frame_hits(n_px)
+    s0 = ctx.frame_ansi()
+    brute = ctx.timings()["sphere_tests"]
+    ctx.render(p, RGB_PIXEL, FLAG_CULL)
+    d1, i1 = ctx.frame_hits(n_px)
+    s1 = ctx.frame_ansi()
+    culled = ctx.timings()["sphere_tests"]
+    assert np.array_equal(i0, i1) and d0.tobytes() == d1.tobytes() and np.array_equal(s0, s1)
+    assert brute >= n_px * 1024 and culled < brute // 4, (brute, culled)
