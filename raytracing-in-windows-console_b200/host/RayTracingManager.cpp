@@ -44,7 +44,8 @@ void RayTracingManager::Update(const RayTracingCPUToGPUData& params, const Devic
     p.cam_pos[0] = params.camPos.x; p.cam_pos[1] = params.camPos.y; p.cam_pos[2] = params.camPos.z;
     p.x = (uint32_t)params.x; p.y = (uint32_t)params.y;
     p.element1 = params.element1; p.element2 = params.element2; p.cam_far = params.camFarDist;
-    uint32_t flags = (m_shadows ? RTC_FLAG_SHADOWS : 0u) | (m_fixLaunchLimit ? 0u : RTC_FLAG_UPDATE_REF_LAUNCH_LIMIT);
+    uint32_t flags = (m_shadows ? RTC_FLAG_SHADOWS : 0u) | (m_culling ? RTC_FLAG_CULL : 0u) |
+                     (m_fixLaunchLimit ? 0u : RTC_FLAG_UPDATE_REF_LAUNCH_LIMIT);
     const char* stream = nullptr;
     size_t size = 0;
     // physics step + trace + shade + ANSI encode + stream to (pinned) host memory

@@ -32,10 +32,12 @@ public:
     // Extensions.  Shadows: opt-in shadow rays (not in the reference).  FixLaunchLimit(true): let
     // UpdateObjects move more than 1024 objects (the reference's launch is rejected there).
     void SetShadows(bool on) { m_shadows = on; }
+    void SetCulling(bool on) { m_culling = on; }      // per-tile sphere culling: identical frames, fewer tests (RTC_FLAG_CULL)
     void FixLaunchLimit(bool on) { m_fixLaunchLimit = on; }
 
 private:
     RenderingMode currentRenderingMode = BIT_ASCII;    // reference RayTracingManager.h:53
     bool m_shadows = false;
+    bool m_culling = false;
     bool m_fixLaunchLimit = false;
 };

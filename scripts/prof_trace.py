@@ -7,10 +7,11 @@ from rtc_b200 import scenes
 
 name = sys.argv[1] if len(sys.argv) > 1 else "config3_4k_1024"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+flags = rtc_b200.FLAG_CULL if (len(sys.argv) > 3 and sys.argv[3] == "cull") else 0
 ctx = rtc_b200.Context(0)
 ctx.set_objects(scenes.config_scene(name))
 p = scenes.config_camera(name)
 for _ in range(n):
-    ctx.render(p, rtc_b200.RGB_PIXEL)
+    ctx.render(p, rtc_b200.RGB_PIXEL, flags)
     ctx.frame_ansi_device()
 print(ctx.timings())
