@@ -294,8 +294,15 @@ def run_ours(args):
         # rank 0's frame planes; rank 0 encodes the assembled frame.  Rank 0 also pays for the encoder, so it gets a
         # smaller band: the deficit (in rows) is measured on rank 0 from one whole frame's stage timings.
         if args.gather == "host":
-            renderer = multigpu.HostAssembledRenderer(ctx, dist, rank, world, x, y, mode)
-        else:
+            # needs a POSIX shared-memory segment that can be page-locked; if any rank cannot have it, every rank
+            # falls back to gathering the planes on GPU 0 over NVLink
+            try:                                   # collective: raises on every rank or on none
+                renderer = multigpu.HostAssembledRenderer(ctx, dist, rank, world, x, y, mode)
+            except RuntimeError as e:
+                sys.stderr.write("rank %d: %s -- falling back to --gather ipc\n" % (rank, e))
+                renderer = None
+                args.gather = "ipc"
+        if renderer is None:
             hdr = [0.0]
             if rank == 0:
                 for _ in range(3):

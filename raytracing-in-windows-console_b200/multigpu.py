@@ -208,21 +208,49 @@ class HostAssembledRenderer:
         self.copy_stream = torch.cuda.Stream()
         self.frame_cap = encode_capacity(x, y, mode)
         size = self.HDR + 2 * self.frame_cap
+        # Set-up is collective: rank 0 creates the segment, everybody maps and page-locks it, and either every rank
+        # succeeds or every rank raises (so that callers can fall back to another gather mode together).
+        self.shm, self._addr, err = None, None, None
         names = [None]
         if rank == 0:
-            self.shm = shared_memory.SharedMemory(create=True, size=size, name=name)
-            names = [self.shm.name]
+            try:
+                self.shm = shared_memory.SharedMemory(create=True, size=size, name=name)
+                names = [self.shm.name]
+            except Exception as e:                                   # noqa: BLE001
+                err = e
         if world > 1:
             dist.broadcast_object_list(names, src=0)
-        if rank != 0:
-            self.shm = shared_memory.SharedMemory(name=names[0])
-        self._addr = ctypes.addressof(ctypes.c_char.from_buffer(self.shm.buf))
-        rc = torch.cuda.cudart().cudaHostRegister(self._addr, size, 1)       # portable; every rank pins its own mapping
-        if int(rc) != 0:
-            raise RuntimeError("cudaHostRegister failed: %s" % rc)
-        hdr = np.frombuffer(self.shm.buf, dtype=np.int64, count=self.HDR // 8)
-        if rank == 0:
-            hdr[:] = 0
+        if names[0] is None and err is None:
+            err = RuntimeError("rank 0 could not create the shared frame segment")
+        if err is None:
+            try:
+                if rank != 0:
+                    self.shm = shared_memory.SharedMemory(name=names[0])
+                    try:                                 # only the creator unlinks; keep Python's tracker from doing it again
+                        from multiprocessing import resource_tracker
+                        resource_tracker.unregister(self.shm._name, "shared_memory")
+                    except Exception:
+                        pass
+                self._addr = ctypes.addressof(ctypes.c_char.from_buffer(self.shm.buf))
+                rc = torch.cuda.cudart().cudaHostRegister(self._addr, size, 1)   # portable; every rank pins its own mapping
+                if int(rc) != 0:
+                    self._addr = None
+                    raise RuntimeError("cudaHostRegister failed: %s" % rc)
+                hdr = np.frombuffer(self.shm.buf, dtype=np.int64, count=self.HDR // 8)
+                if rank == 0:
+                    hdr[:] = 0
+            except Exception as e:                                   # noqa: BLE001
+                err = e
+        if world > 1:
+            oks = [None] * world
+            dist.all_gather_object(oks, err is None)                  # also the "header is zeroed" barrier
+            if not all(oks) and err is None:
+                err = RuntimeError("another rank could not set up the shared frame segment")
+        if err is not None:
+            self.lens = self.len_tag = self.done_tag = self.consumed = self.frames = None
+            hdr = None
+            self.close()
+            raise RuntimeError("host-assembled frames unavailable: %r" % (err,))
         # per slot: lens[world], len_tag[world], done_tag[world]; then consumed_tag[2]
         self.lens = [hdr[(3 * s) * 16:(3 * s) * 16 + world] for s in range(2)]
         self.len_tag = [hdr[(3 * s + 1) * 16:(3 * s + 1) * 16 + world] for s in range(2)]
@@ -230,8 +258,6 @@ class HostAssembledRenderer:
         self.consumed = hdr[96:98]
         self.frames = [torch.frombuffer(self.shm.buf, dtype=torch.uint8, count=self.frame_cap,
                                         offset=self.HDR + s * self.frame_cap) for s in range(2)]
-        if world > 1:
-            dist.barrier()                                                # header zeroed before anyone polls it
         self.k_sub = 0
         self.k_col = 0
         self.k_step = 0
@@ -307,14 +333,18 @@ class HostAssembledRenderer:
         return self.frames[slot][:total], total
 
     def close(self):
-        try:
-            self.torch.cuda.cudart().cudaHostUnregister(self._addr)
-        except Exception:
-            pass
+        if getattr(self, "_addr", None) is not None:
+            try:
+                self.torch.cuda.cudart().cudaHostUnregister(self._addr)
+            except Exception:
+                pass
+            self._addr = None
         self.lens = self.len_tag = self.done_tag = self.consumed = self.frames = None
-        try:
-            self.shm.close()
-            if self.rank == 0:
-                self.shm.unlink()
-        except Exception:
-            pass
+        if getattr(self, "shm", None) is not None:
+            try:
+                self.shm.close()
+                if self.rank == 0:
+                    self.shm.unlink()
+            except Exception:
+                pass
+            self.shm = None
