@@ -105,8 +105,6 @@ struct rtc_ctx {
     DevBuf<float> d_dmin, d_dmin_l;   // per group of 4 spheres: lower bound of any hit distance (camera / light origin)
     DevBuf<float4> d_cone, d_cone_l;  // per group: bounding cone seen from the origin (axis, cos half-angle) ...
     DevBuf<float> d_sin, d_sin_l;     // ... and the sine of its half-angle (RTC_FLAG_CULL)
-    bool last_cull = false;
-    uint64_t last_rays = 0, last_spheres = 0;
     DevBuf<float> d_fast_l;    // the same hoist with the light as origin (shadow-ray extension)
     DevBuf<float4> d_exact_l;
     DevBuf<uint8_t> d_shadow;  // 1 byte per pixel: occluded
@@ -118,7 +116,8 @@ struct rtc_ctx {
     DevBuf<char> d_out[2];                  // two frame slots: the stream of frame k is copied out while k+1 is encoded
     DevBuf<unsigned char> d_desc;           // encoder scratch: per-tile counts, group accumulators (two parities)
     uint32_t enc_parity = 0;
-    DevBuf<unsigned int> d_counters;        // [0..31] trace tile tickets, [32] encode ticket (never reset)
+    DevBuf<unsigned int> d_counters;        // zeroed by the hoist every frame: [0..27] tile tickets of the primary pass (one per
+                                            // sphere chunk), [32..59] of the shadow pass, [60..63] two 64-bit counts of groups tested
     DevBuf<unsigned long long> d_total;     // [2]
     DevBuf<float> d_sink;
     PinBuf<unsigned long long> h_total;     // [2]
@@ -278,7 +277,7 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
     unsigned long long* stats = reinterpret_cast<unsigned long long*>(c->d_counters.p + rtc::kStatsCounter);   // zeroed by the hoist
     CK(rtc::launch_hoist(c->stream, c->d_objs.p, c->d_sphere_obj.p, n_spheres, n_slots, p->cam_pos, c->d_fast.p,
                          c->d_exact.p, c->d_dmin.p, c->d_cone.p, c->d_sin.p, c->d_counters.p, rtc::kNumCounters));
-    c->last_cull = cull; c->last_rays = (uint64_t)n_px; c->last_spheres = (uint64_t)n_spheres;
+
     c->last_launches++;
     const bool shadows = (flags & RTC_FLAG_SHADOWS) != 0 && mode != RTC_SDL && mode != RTC_RGB_NORMALS;
     if (shadows) {
@@ -298,7 +297,7 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
         const rtc::FrameParams fp = make_frame(p, row0, row1);
         const rtc::TracePlan plan = rtc::plan_trace(p->x, row1 - row0, n_slots, c->sm_count);
         const int n_chunks = n_slots == 0 ? 1 : (n_slots + plan.max_slots - 1) / plan.max_slots;
-        if (n_chunks > 32) return fail(RTC_ERR_CAPACITY, "too many spheres (%d)", n_spheres);
+        if (n_chunks > 28) return fail(RTC_ERR_CAPACITY, "too many spheres (%d)", n_spheres);
         for (int ch = 0; ch < n_chunks; ++ch) {
             const int s0 = ch * plan.max_slots;
             const int slots = n_slots - s0 < plan.max_slots ? n_slots - s0 : plan.max_slots;

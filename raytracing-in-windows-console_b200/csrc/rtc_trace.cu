@@ -7,9 +7,9 @@
 //   * All primary rays share the origin (RayTracing.cu:195), so oc = origin - centre and
 //     c = |oc|^2 - r^2 are per-sphere, per-frame constants: kernel 0 hoists them (bit-identical
 //     to what the reference recomputes per ray).
-//   * Kernel 1 is persistent: one CTA of 16..28 warps per SM (plan_trace picks the count from the number
-//     of tiles) keeps the sphere list (2156..4788 spheres per launch; longer lists are chunked) in shared
-//     memory and walks 16x16-pixel screen tiles, one tile per warp, 8 rays per thread.
+//   * Kernel 1 is persistent: one CTA of 24 or 28 warps per SM (plan_trace picks from the number of tiles)
+//     keeps the sphere list (2500 / 1776 spheres per launch; longer lists are chunked) in shared memory and
+//     walks 16x16-pixel screen tiles, one tile per warp, 8 rays per thread.
 //   * The inner loop tests TWO spheres against one ray per packed instruction (FMUL2/FFMA2).
 //     Measured on B200: an FFMA2 only sustains 1 per 2 cycles when at most one operand pair is
 //     fresh (register-bank limit), and every ALU-pipe instruction (FMNMX3, FSETP, ...) costs
@@ -24,6 +24,10 @@
 //     decisions and distances are bit-identical to the reference.
 //   * The running best (distance, object index) per ray lives in shared memory: it is touched
 //     only on the (rare) exact path and would otherwise cost 16 registers in the hot loop.
+//   * Sphere slots are in Morton order (host), 4 neighbours per packed group; per group the hoist also
+//     produces a lower bound of any hit distance (rays that already have a nearer hit skip the group's
+//     exact path) and a bounding cone (RTC_FLAG_CULL: warp tiles skip groups their ray cone misses).
+//   * The shadow-ray extension is the same kernel with the light as the common origin (SHADOW = true).
 #include <cstdlib>
 
 #include "rtc_device.cuh"

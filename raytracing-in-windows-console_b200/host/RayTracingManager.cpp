@@ -27,7 +27,7 @@ RayTracingManager::RayTracingManager()
     gpuErrchk(rtc_resize(Scene3D::Context(), (uint32_t)PrintMachine::GetWidth(), (uint32_t)PrintMachine::GetHeight()));
 }
 
-RayTracingManager::~RayTracingManager() {}
+RayTracingManager::~RayTracingManager() {}   // (a frame still in flight is dropped with the context)
 
 void RayTracingManager::SetRenderingMode(const RenderingMode newRenderMode) { currentRenderingMode = newRenderMode; }
 
@@ -48,7 +48,33 @@ void RayTracingManager::Update(const RayTracingCPUToGPUData& params, const Devic
                      (m_fixLaunchLimit ? 0u : RTC_FLAG_UPDATE_REF_LAUNCH_LIMIT);
     const char* stream = nullptr;
     size_t size = 0;
+    m_ctx = ctx;
+    if (m_pipelined) {
+        gpuErrchk(rtc_submit(ctx, &p, (rtc_mode)currentRenderingMode, dt, flags));   // frame k
+        if (m_inFlight) {                                                            // frame k-1
+            gpuErrchk(rtc_collect(ctx, &stream, &size));
+            PrintMachine::SetDataInBackBuffer(stream, size);
+        }
+        m_inFlight = true;
+        return;
+    }
     // physics step + trace + shade + ANSI encode + stream to (pinned) host memory
     gpuErrchk(rtc_update(ctx, &p, (rtc_mode)currentRenderingMode, dt, flags, &stream, &size));
     PrintMachine::SetDataInBackBuffer(stream, size);             // reference RayTracingManager.cu:150
+}
+
+void RayTracingManager::SetPipelined(bool on)
+{
+    if (!on) Flush();
+    m_pipelined = on;
+}
+
+void RayTracingManager::Flush()
+{
+    if (!m_inFlight || !m_ctx) return;
+    const char* stream = nullptr;
+    size_t size = 0;
+    gpuErrchk(rtc_collect(reinterpret_cast<rtc_ctx*>(m_ctx), &stream, &size));
+    PrintMachine::SetDataInBackBuffer(stream, size);
+    m_inFlight = false;
 }

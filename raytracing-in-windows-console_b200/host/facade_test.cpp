@@ -2,6 +2,7 @@
 // and dumps what lands in PrintMachine's back buffer, for the parity tests (tests/test_facade.py).
 //   facade_test <outdir>           -> default scene, 240x64, every mode  -> <outdir>/default_240x64_m<k>.bin
 //   facade_test <outdir> engine N  -> Engine3D::Start(240,64) + N frames (dt = 0) in RGB_PIXEL
+//   facade_test <outdir> pipelined N -> the same through the pipelined sink (SetPipelined + Flush), culling on
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -21,14 +22,17 @@ int main(int argc, char** argv)
 {
     if (argc < 2) { fprintf(stderr, "usage: facade_test <outdir> [engine N]\n"); return 2; }
     const std::string out = argv[1];
-    if (argc >= 4 && !strcmp(argv[2], "engine")) {
+    if (argc >= 4 && (!strcmp(argv[2], "engine") || !strcmp(argv[2], "pipelined"))) {
+        const bool pipelined = !strcmp(argv[2], "pipelined");
         Engine3D engine;
         engine.Start(240, 64);
         engine.SetFixedDt(0.0);
         engine.Manager().SetRenderingMode(RGB_PIXEL);
+        if (pipelined) { engine.Manager().SetPipelined(true); engine.Manager().SetCulling(true); }
         const int n = atoi(argv[3]);
         for (int i = 0; i < n && engine.Run(); ++i) {}
-        dump(out + "/engine_240x64_m3.bin");
+        engine.Manager().Flush();
+        dump(out + (pipelined ? "/pipelined_240x64_m3.bin" : "/engine_240x64_m3.bin"));
         engine.CleanUp();
         return 0;
     }

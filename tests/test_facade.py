@@ -29,7 +29,7 @@ def test_facade_exposes_reference_api():
         "Camera3D::Init()", "Camera3D::Update()", "Camera3D::GetInverseVMatrix() const", "Camera3D::Move(long double)",
         "Camera3D::AddRot(long double, short, short, short)", "Camera3D::SetPos(float, float, float)",
         "RayTracingManager::Update(RayTracingCPUToGPUData const&, DeviceObjectArray<Object3D*> const&, double)",
-        "RayTracingManager::SetRenderingMode(RenderingMode)",
+        "RayTracingManager::SetRenderingMode(RenderingMode)", "RayTracingManager::SetPipelined(bool)", "RayTracingManager::Flush()",
         "PrintMachine::Start(unsigned long, unsigned long)", "PrintMachine::SetDataInBackBuffer(char const*, unsigned long)",
         "PrintMachine::GetBackBuffer()", "PrintMachine::GetMaxSize()", "PrintMachine::Print()",
     ]:
@@ -46,6 +46,10 @@ def test_facade_frames_match_reference(golden, tmp_path):
         assert np.array_equal(got, golden[f"default_240x64_m{mode}_stream"]), f"mode {mode}"
     subprocess.check_call([os.path.join(HOST, "facade_test"), str(tmp_path), "engine", "3"])
     got = np.fromfile(tmp_path / "engine_240x64_m3.bin", np.uint8)
+    assert np.array_equal(got, golden["default_240x64_m3_stream"])
+    # pipelined sink (rtc_submit / rtc_collect behind RayTracingManager::Update) + per-tile culling: same bytes
+    subprocess.check_call([os.path.join(HOST, "facade_test"), str(tmp_path), "pipelined", "4"])
+    got = np.fromfile(tmp_path / "pipelined_240x64_m3.bin", np.uint8)
     assert np.array_equal(got, golden["default_240x64_m3_stream"])
 
 
