@@ -8,7 +8,7 @@
 //     c = |oc|^2 - r^2 are per-sphere, per-frame constants: kernel 0 hoists them (bit-identical
 //     to what the reference recomputes per ray).
 //   * Kernel 1 is persistent: one CTA of 24 or 28 warps per SM (plan_trace picks from the number of tiles)
-//     keeps the sphere list (2500 / 1776 spheres per launch; longer lists are chunked) in shared memory and
+//     keeps the sphere list (2496 / 1772 spheres per launch; longer lists are chunked) in shared memory and
 //     walks 16x16-pixel screen tiles, one tile per warp, 8 rays per thread.
 //   * The inner loop tests TWO spheres against one ray per packed instruction (FMUL2/FFMA2).
 //     Measured on B200: an FFMA2 only sustains 1 per 2 cycles when at most one operand pair is
