@@ -176,6 +176,9 @@ RTC_API int rtc_frame_ansi_device(rtc_ctx* ctx, const char** dev_ptr, size_t* n_
 RTC_API int rtc_frame_color(rtc_ctx* ctx, const uint8_t** host_color, uint32_t* bpp,
                             const uint8_t** host_glyph);
 RTC_API int rtc_frame_hits(rtc_ctx* ctx, const float** host_dist, const int32_t** host_index);
+/* Parity hook: the shade kernel's xterm-256 quantiser (== ansi256_from_rgb, ANSIRGB.h:141-189) evaluated over the whole
+ * RGB cube into 2^24 bytes of DEVICE memory, dev_out[(r << 16) | (g << 8) | b]; asynchronous on the context's stream. */
+RTC_API int rtc_debug_ansi256_cube(rtc_ctx* ctx, uint8_t* dev_out);
 /* RayTracingManager::Update as one synchronous call: optional physics step (dt != 0),
  * render, copy the stream to host.                                                        */
 RTC_API int rtc_update(rtc_ctx* ctx, const rtc_params* params, rtc_mode mode, double dt,

@@ -22,7 +22,7 @@ EXPORTS = [
     "rtc_create", "rtc_destroy", "rtc_last_error", "rtc_version", "rtc_set_stream", "rtc_device_info",
     "rtc_resize", "rtc_scene_clear", "rtc_scene_add_sphere", "rtc_scene_add_plane", "rtc_scene_set_objects",
     "rtc_scene_get_objects", "rtc_scene_count", "rtc_update_objects", "rtc_render", "rtc_frame_ansi",
-    "rtc_frame_ansi_device", "rtc_frame_color", "rtc_frame_hits", "rtc_update", "rtc_submit", "rtc_collect", "rtc_last_timings",
+    "rtc_frame_ansi_device", "rtc_frame_color", "rtc_frame_hits", "rtc_debug_ansi256_cube", "rtc_update", "rtc_submit", "rtc_collect", "rtc_last_timings",
     "rtc_trace_band", "rtc_encode", "rtc_encode_band", "rtc_encode_capacity", "rtc_mode_bpp", "rtc_mode_has_glyph",
     "rtc_ipc_export", "rtc_ipc_open", "rtc_ipc_close", "rtc_camera_params", "rtc_fp32_peak",
 ]
@@ -72,6 +72,7 @@ def load_library(build_if_missing=True):
     L.rtc_frame_ansi_device.argtypes = [vp, c.POINTER(vp), c.POINTER(sz)]
     L.rtc_frame_color.argtypes = [vp, c.POINTER(vp), c.POINTER(u32), c.POINTER(vp)]
     L.rtc_frame_hits.argtypes = [vp, c.POINTER(vp), c.POINTER(vp)]
+    L.rtc_debug_ansi256_cube.argtypes = [vp, vp]
     L.rtc_update.argtypes = [vp, vp, i32, f64, u32, c.POINTER(vp), c.POINTER(sz)]
     L.rtc_submit.argtypes = [vp, vp, i32, f64, u32]
     L.rtc_collect.argtypes = [vp, c.POINTER(vp), c.POINTER(sz)]
@@ -203,6 +204,9 @@ class Context:
         pd, pi = ctypes.c_void_p(), ctypes.c_void_p()
         _check(self.L.rtc_frame_hits(self._h, ctypes.byref(pd), ctypes.byref(pi)))
         return _view(pd.value, n_px, np.float32).copy(), _view(pi.value, n_px, np.int32).copy()
+
+    def ansi256_cube(self, dev_out):
+        _check(self.L.rtc_debug_ansi256_cube(self._h, ctypes.c_void_p(dev_out)))
 
     def update(self, params, mode, dt=0.0, flags=0):
         """RayTracingManager::Update: physics step + render + stream to host."""

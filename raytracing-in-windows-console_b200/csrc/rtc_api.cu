@@ -743,6 +743,14 @@ int rtc_encode_band(rtc_ctx* c, const uint8_t* dev_color, const uint8_t* dev_gly
     return RTC_OK;
 }
 
+int rtc_debug_ansi256_cube(rtc_ctx* c, uint8_t* dev_out)
+{
+    if (!c || !dev_out) return fail(RTC_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    CK(rtc::launch_ansi256_cube(c->stream, dev_out));
+    return RTC_OK;
+}
+
 int rtc_ipc_export(rtc_ctx* c, void* dev_ptr, unsigned char handle_out[64])
 {
     if (!c || !dev_ptr || !handle_out) return fail(RTC_ERR_INVALID, "NULL argument");

@@ -33,6 +33,8 @@ cudaError_t launch_shade(cudaStream_t st, const FrameParams& fp, int mode, uint3
                          const rtc_object* objs, int n_objs, const float* hit_t, const int32_t* hit_idx,
                          const uint8_t* shadow /* NULL: every point is lit */, uint8_t* color, uint8_t* glyph);
 
+cudaError_t launch_ansi256_cube(cudaStream_t st, uint8_t* out /* 2^24 bytes */);
+
 // kernel 3 (rtc_encode.cu)
 cudaError_t configure_encode();
 size_t encode_state_bytes(uint64_t n_cells);

@@ -401,3 +401,32 @@ def test_culling_is_invisible(ctx, oracle, rtc):
     culled = ctx.timings()["sphere_tests"]
     assert np.array_equal(i0, i1) and d0.tobytes() == d1.tobytes() and np.array_equal(s0, s1)
     assert brute >= n_px * 1024 and culled < brute // 4, (brute, culled)
+
+
+def test_quantisers_exhaustive(ctx, oracle, rtc):
+    """The integer quantisers over their whole domains: xterm-256 index of all 2^24 RGB values (shade kernel) and the
+    NUL-padded decimal digits of all 256 byte values in every channel position (encoder), against the oracle (which
+    tests/test_oracle_vs_reference.py pins exhaustively against the reference)."""
+    import torch
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    cube = torch.empty(1 << 24, dtype=torch.uint8, device="cuda")
+    ctx.ansi256_cube(cube.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(cube.cpu().numpy(), oracle.ansi256_range(0, 1 << 24))
+    # every byte value in every channel, each cell different from its neighbour: 3 x 256 cells + 8-bit mode 256 cells
+    v = np.arange(256, dtype=np.uint8)
+    z = np.zeros(256, np.uint8)
+    rgb = np.concatenate([np.stack([v, z, z], 1), np.stack([z + 7, v, z], 1), np.stack([z, z + 9, v], 1)]).reshape(-1)
+    for mode, keys, x, y in ((RGB_PIXEL, rgb, 257, 3), (RGB_ASCII, rgb, 129, 6), (BIT_PIXEL, v, 65, 4), (BIT_ASCII, v, 257, 1)):
+        W = x - 1
+        glyph = (np.arange(W * y) % 5 == 0).astype(np.uint8) * 3 + 32 if mode_has_glyph(mode) else None
+        dk = torch.from_numpy(keys.copy()).cuda()
+        dg = torch.from_numpy(glyph).cuda() if glyph is not None else None
+        cap = rtc.encode_capacity(x, y, mode)
+        out = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+        total = torch.zeros(1, dtype=torch.int64, device="cuda")
+        ctx.encode(dk.data_ptr(), dg.data_ptr() if dg is not None else 0, x, y, mode, out.data_ptr(), cap, total.data_ptr())
+        torch.cuda.synchronize()
+        got = out[:int(total.item())].cpu().numpy()
+        assert np.array_equal(got, oracle.encode_planes(keys, glyph, x, y, mode)), MODE_NAMES[mode]
+    ctx.set_stream(0)
