@@ -430,3 +430,34 @@ def test_quantisers_exhaustive(ctx, oracle, rtc):
         got = out[:int(total.item())].cpu().numpy()
         assert np.array_equal(got, oracle.encode_planes(keys, glyph, x, y, mode)), MODE_NAMES[mode]
     ctx.set_stream(0)
+
+
+def test_random_scenes_sweep(ctx, oracle, rtc):
+    """Seeded sweep of small frames: random sphere clouds (radius 0 included, overlapping and nested spheres), planes
+    of either facing, cameras outside / inside the cloud / inside a sphere, arbitrary rotations and pixel aspects,
+    every flag combination -- hit records bit-exact, colours and stream as in check_frame."""
+    rng = np.random.default_rng(2024)
+    for case in range(72):
+        n = int(rng.integers(1, 400))
+        objs = scenes.random_spheres(n, 1000 + case)
+        if case % 3 == 0:                                            # nested / coincident spheres, exact distance ties
+            objs[: n // 2]["center"] = objs[n // 2: 2 * (n // 2)]["center"]
+        extra = []
+        if case % 2 == 0:
+            extra.append(scenes.make_plane((0, float(rng.integers(-70, -20)), 0), (0, 1, 0), (100, 100, 100), 300, 300))
+        if case % 4 == 1:
+            extra.append(scenes.make_plane((0, 0, 40), (0.3, 0.2, -1.0), (10, 200, 100), 120, 90))
+        if extra:
+            objs = np.concatenate([objs, np.array(extra, OBJECT_DTYPE)])
+        x, y = int(rng.integers(18, 150)), int(rng.integers(5, 70))
+        if case % 5 == 0:
+            pos = tuple(float(v) for v in rng.uniform(-40, 40, 3))   # inside the cloud
+        elif case % 5 == 1:
+            c0 = objs[0]["center"]; pos = (float(c0[0]) + 0.1, float(c0[1]), float(c0[2]))   # inside / on a sphere
+        else:
+            pos = tuple(float(v) for v in rng.uniform(-1, 1, 3) * 60 + np.array([0, 0, -130]))
+        rot = (float(rng.uniform(-0.6, 0.6)), float(PI32 + rng.uniform(-0.8, 0.8)), 0.0)
+        p = rtc.camera_params(x, y, pos, rot, float(rng.choice([0.0, 1.0 / (x - 1), 0.02])))
+        mode = [RGB_PIXEL, RGB_ASCII, BIT_PIXEL, BIT_ASCII, RGB_NORMALS][case % 5]
+        flags = [0, FLAG_CULL, FLAG_SHADOWS, FLAG_CULL | FLAG_SHADOWS][case % 4]
+        check_frame(ctx, oracle, objs, p, mode, flags=flags)
