@@ -297,7 +297,7 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
         const rtc::FrameParams fp = make_frame(p, row0, row1);
         const rtc::TracePlan plan = rtc::plan_trace(p->x, row1 - row0, n_slots, c->sm_count);
         const int n_chunks = n_slots == 0 ? 1 : (n_slots + plan.max_slots - 1) / plan.max_slots;
-        if (n_chunks > 28) return fail(RTC_ERR_CAPACITY, "too many spheres (%d)", n_spheres);
+        if (n_chunks > rtc::kMaxChunks) return fail(RTC_ERR_CAPACITY, "too many spheres (%d)", n_spheres);
         for (int ch = 0; ch < n_chunks; ++ch) {
             const int s0 = ch * plan.max_slots;
             const int slots = n_slots - s0 < plan.max_slots ? n_slots - s0 : plan.max_slots;

@@ -13,6 +13,7 @@ struct FrameParams;
 struct TracePlan { int threads; int max_slots; };   // threads per CTA; sphere slots resident in shared memory per launch
 TracePlan plan_trace(uint32_t x, uint32_t rows, int n_slots, int n_ctas);
 constexpr int kNumCounters = 64;           // per-frame device counters zeroed by the hoist kernel
+constexpr int kMaxChunks = 28;             // sphere-list chunks per pass (one tile ticket each): 69k spheres at 24 warps
 constexpr int kStatsCounter = 60;          // [60..63]: two 64-bit counts of sphere groups tested (primary, shadow pass)
 
 // kernel 0 / 1 (rtc_trace.cu)

@@ -518,6 +518,7 @@ TracePlan plan_trace(uint32_t x, uint32_t rows, int n_slots, int n_ctas)
         if (force && atoi(force) != w * 32) continue;
         const int max_slots = (int)((227 * 1024 - 96 - (long long)w * 32 * (6 * kRays * 4)) / 34) & ~3;
         const int chunks = n_slots <= max_slots ? 1 : (n_slots + max_slots - 1) / max_slots;
+        if (chunks > kMaxChunks && w > 24) continue;                   // (the API refuses more chunks than it has tickets for)
         const long long per_wave = (long long)n_ctas * w;
         const double waves = (double)((tiles + per_wave - 1) / per_wave);
         // per chunk: the sphere loop over its share of the list + a fixed ray set-up / write-back worth ~40 sphere tests

@@ -298,6 +298,15 @@ def test_many_spheres_chunked(ctx, oracle, rtc):
     check_frame(ctx, oracle, objs, p, RGB_PIXEL, flags=FLAG_SHADOWS)
 
 
+def test_reference_scene_capacity(ctx, oracle, rtc):
+    """The reference's typed sphere array holds 52,083 spheres (5 MB / 96 B, Scene3D.cpp:131-141): a scene of that size
+    goes through ~21 shared-memory chunks per pass."""
+    objs = scenes.random_spheres(52083, 41)
+    p = rtc.camera_params(34, 9, (0, 0, -120), (0, PI32, 0), 1.0 / 33)
+    check_frame(ctx, oracle, objs, p, RGB_PIXEL)
+    check_frame(ctx, oracle, objs, p, RGB_PIXEL, flags=FLAG_CULL | FLAG_SHADOWS)
+
+
 def test_shadow_pass_config2(ctx, oracle):
     """BASELINE config 2 (1921x1080, 64 spheres + plane, primary + shadow rays): the light-origin shadow pass
     (trace_kernel<true>: packed filter + exact path) against the oracle's definition, whole frame, two modes."""
