@@ -48,6 +48,16 @@ def parse_args():
     return ap.parse_args()
 
 
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.lower().startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
 def ncu_traffic():
     """DRAM bytes per launch of our kernels from the committed ncu --set full captures (profiles/)."""
     path = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
@@ -229,7 +239,8 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * frame_rays / (value * 1e6),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "mode": args.mode, "note": "ms_per_step = whole-frame time extrapolated from the sample rate"},
-        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": last["cores"], "kind": last["kind"], "sample": last["sample"],
+                         "cpu_model": cpu_model()},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "frames_per_s": value * 1e6 / frame_rays,
         "gpu_launches": 0,
@@ -551,7 +562,8 @@ def run_ours(args):
             line["ref_cuda_sm100"] = ref_cuda_sample(name, mode)
             try:
                 cb = cpu_reference_sample(name, mode, args.cpu_seconds)
-                line["cpu_baseline"] = {"value": cb["mrays_s"], "unit": "Mrays/s", "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]}
+                line["cpu_baseline"] = {"value": cb["mrays_s"], "unit": "Mrays/s", "cores": cb["cores"], "kind": cb["kind"],
+                                        "sample": cb["sample"], "cpu_model": cpu_model()}
             except Exception as e:  # the checker being absent must not hide the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
     else:
