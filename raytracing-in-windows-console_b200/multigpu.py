@@ -174,14 +174,17 @@ class HostAssembledRenderer:
     it.  The frame is assembled where the reference's sink wants it -- in host memory (PrintMachine::
     SetDataInBackBuffer) -- by 1/2/4/8 copy engines in parallel instead of one.
 
-      submit(params)  enqueue trace + shade + encode of this rank's band (two frames may be in flight)
+      submit(params)  enqueue trace + shade + encode of this rank's band (up to three frames in flight)
       collect()       oldest frame: publish this rank's stream length, wait for the lengths of the ranks before it,
                       D2H the band stream into the shared frame; on rank 0 also wait for every rank and return
-                      (uint8 view of the frame, n_bytes), valid until the second submit after this call.
+                      (uint8 view of the frame, n_bytes), valid until the second collect after this one.
+    With three frames in flight (submit, submit, then submit + collect per frame) the copy of frame k+1 is issued
+    while frame k is being returned and overlaps both the kernels of frame k+2 and the host work of the next submit.
     Cross-process state lives in the shared segment (lengths and frame tags); ranks poll it from the host.
     """
 
     HDR = 4096
+    NS = 3                      # frame slots: frame j lives in slot j % NS
 
     def __init__(self, ctx, dist, rank, world, x, y, mode, name=None):
         import ctypes
@@ -189,6 +192,7 @@ class HostAssembledRenderer:
         import numpy as np
         import torch
         from . import encode_capacity, mode_bpp, mode_has_glyph
+        NS = self.NS
         self.torch, self.np, self.ctx, self.rank, self.world = torch, np, ctx, rank, world
         self.x, self.y, self.W, self.mode = x, y, x - 1, mode
         self.bpp, self.gl = mode_bpp(mode), bool(mode_has_glyph(mode))
@@ -201,13 +205,14 @@ class HostAssembledRenderer:
         self.color = torch.empty(rows_t * W * bpp + 64, **u8)
         self.glyph = torch.empty(rows_t * W + 64, **u8) if self.gl else None
         self.band_cap = encode_capacity(x, max(1, self.r1 - self.r0), mode)
-        self.out = [torch.empty(self.band_cap, **u8) for _ in range(2)]
-        self.total = torch.zeros(2, dtype=torch.int64, device="cuda")
-        self.h_total = torch.zeros(2, dtype=torch.int64).pin_memory()
-        self.done_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        self.out = [torch.empty(self.band_cap, **u8) for _ in range(NS)]
+        self.total = torch.zeros(NS, dtype=torch.int64, device="cuda")
+        self.h_total = torch.zeros(NS, dtype=torch.int64).pin_memory()
+        self.done_ev = [torch.cuda.Event() for _ in range(NS)]
+        self.copy_ev = [torch.cuda.Event() for _ in range(NS)]
         self.copy_stream = torch.cuda.Stream()
         self.frame_cap = encode_capacity(x, y, mode)
-        size = self.HDR + 2 * self.frame_cap
+        size = self.HDR + NS * self.frame_cap
         # Set-up is collective: rank 0 creates the segment, everybody maps and page-locks it, and either every rank
         # succeeds or every rank raises (so that callers can fall back to another gather mode together).
         self.shm, self._addr, err = None, None, None
@@ -222,6 +227,7 @@ class HostAssembledRenderer:
             dist.broadcast_object_list(names, src=0)
         if names[0] is None and err is None:
             err = RuntimeError("rank 0 could not create the shared frame segment")
+        hdr = None
         if err is None:
             try:
                 if rank != 0:
@@ -247,28 +253,25 @@ class HostAssembledRenderer:
             if not all(oks) and err is None:
                 err = RuntimeError("another rank could not set up the shared frame segment")
         if err is not None:
-            self.lens = self.len_tag = self.done_tag = self.consumed = self.frames = None
+            self.lens = self.len_tag = self.done_tag = self.released = self.frames = None
             hdr = None
             self.close()
             raise RuntimeError("host-assembled frames unavailable: %r" % (err,))
-        # per slot: lens[world], len_tag[world], done_tag[world]; then consumed_tag[2]
-        self.lens = [hdr[(3 * s) * 16:(3 * s) * 16 + world] for s in range(2)]
-        self.len_tag = [hdr[(3 * s + 1) * 16:(3 * s + 1) * 16 + world] for s in range(2)]
-        self.done_tag = [hdr[(3 * s + 2) * 16:(3 * s + 2) * 16 + world] for s in range(2)]
-        self.consumed = hdr[96:98]
+        # header (int64): per slot lens[16], len_tag[16], done_tag[16]; then released[1]
+        self.lens = [hdr[(3 * s) * 16:(3 * s) * 16 + world] for s in range(NS)]
+        self.len_tag = [hdr[(3 * s + 1) * 16:(3 * s + 1) * 16 + world] for s in range(NS)]
+        self.done_tag = [hdr[(3 * s + 2) * 16:(3 * s + 2) * 16 + world] for s in range(NS)]
+        self.released = hdr[3 * NS * 16:3 * NS * 16 + 1]              # highest frame tag whose buffer may be overwritten
         self.frames = [torch.frombuffer(self.shm.buf, dtype=torch.uint8, count=self.frame_cap,
-                                        offset=self.HDR + s * self.frame_cap) for s in range(2)]
-        self.k_sub = 0
-        self.k_col = 0
-        self.k_step = 0
-        self.pending = []
-        self.t_wait_gpu = self.t_wait_len = self.t_copy = self.t_wait_done = 0.0
+                                        offset=self.HDR + s * self.frame_cap) for s in range(NS)]
+        self.k_sub = self.k_issue = self.k_col = self.k_step = 0
+        self.t_wait_gpu = self.t_wait_len = self.t_copy = self.t_wait_done = self.t_submit = 0.0
 
     def step(self, params, flags=0, slot=None):
         """Device work of one frame (what `value` times): trace + shade + encode of this rank's band."""
         ctx, W, bpp = self.ctx, self.W, self.bpp
         if slot is None:                           # free-running (device-timed loop): any slot will do
-            slot = self.k_step & 1
+            slot = self.k_step % self.NS
             self.k_step += 1
         rows = self.r1 - self.r0
         ctx.trace_band(params, self.mode, self.c0, self.r1, self.color.data_ptr(), self.glyph.data_ptr() if self.gl else 0, flags)
@@ -280,16 +283,15 @@ class HostAssembledRenderer:
     def submit(self, params, flags=0):
         import time
         torch = self.torch
+        if self.k_sub - self.k_col >= self.NS:
+            raise RuntimeError("%d frames are already in flight: collect one first" % self.NS)
         t0 = time.perf_counter()
-        slot = self.k_sub & 1                      # frame j of the submit/collect sequence lives in slot j & 1
+        slot = self.k_sub % self.NS                # frame j of the submit/collect sequence lives in slot j % NS
         self.k_sub += 1
         self.step(params, flags, slot)
-        t1 = time.perf_counter()
         self.h_total[slot:slot + 1].copy_(self.total[slot:slot + 1], non_blocking=True)
         self.done_ev[slot].record(torch.cuda.current_stream())
-        self.pending.append(slot)                 # collect() takes frames in submission order, whatever step() did in between
-        self.t_submit_step = getattr(self, "t_submit_step", 0.0) + (t1 - t0)
-        self.t_submit_rest = getattr(self, "t_submit_rest", 0.0) + (time.perf_counter() - t1)
+        self.t_submit += time.perf_counter() - t0
         return slot
 
     def _spin(self, cond):
@@ -299,12 +301,11 @@ class HostAssembledRenderer:
             if time.perf_counter() - t0 > 60.0:
                 raise RuntimeError("rank %d: timed out waiting for a peer in the shared frame header" % self.rank)
 
-    def collect(self):
-        torch = self.torch
-        k = self.k_col
-        self.k_col += 1
+    def _issue(self, j):
+        """Frame j: wait for its kernels, publish its length, find its offset, start its copy into the shared frame."""
         import time
-        slot, tag, g = self.pending.pop(0), k + 1, self.rank
+        torch = self.torch
+        slot, tag, g = j % self.NS, j + 1, self.rank
         t0 = time.perf_counter()
         self.done_ev[slot].synchronize()
         t1 = time.perf_counter()
@@ -313,24 +314,43 @@ class HostAssembledRenderer:
         self.len_tag[slot][g] = tag
         self._spin(lambda: all(self.len_tag[slot][h] >= tag for h in range(g)))
         off = int(sum(int(self.lens[slot][h]) for h in range(g)))
-        # the frame two back used this slot: wait until rank 0 has released it
-        if k >= 2 and g != 0:
-            self._spin(lambda: self.consumed[slot] >= tag - 2)
+        if j >= self.NS and g != 0:                # frame j - NS used this slot: wait until rank 0 has released it
+            self._spin(lambda: self.released[0] >= tag - self.NS)
         t2 = time.perf_counter()
         if n:
             with torch.cuda.stream(self.copy_stream):
                 self.frames[slot][off:off + n].copy_(self.out[slot][:n], non_blocking=True)
-            self.copy_stream.synchronize()
-        t3 = time.perf_counter()
+        self.copy_ev[slot].record(self.copy_stream)
+        self.t_wait_gpu += t1 - t0
+        self.t_wait_len += t2 - t1
+        self.k_issue = j + 1
+
+    def collect(self):
+        import time
+        if self.k_col >= self.k_sub:
+            raise RuntimeError("no frame in flight")
+        j = self.k_col
+        slot, tag, g = j % self.NS, j + 1, self.rank
+        if self.k_issue <= j:
+            self._issue(j)
+        t0 = time.perf_counter()
+        self.copy_ev[slot].synchronize()
+        t1 = time.perf_counter()
         self.done_tag[slot][g] = tag
-        self.t_wait_gpu += t1 - t0; self.t_wait_len += t2 - t1; self.t_copy += t3 - t2
-        if g != 0:
-            return None, 0
-        self._spin(lambda: all(self.done_tag[slot][h] >= tag for h in range(self.world)))
-        self.t_wait_done += time.perf_counter() - t3
-        total = int(sum(int(self.lens[slot][h]) for h in range(self.world)))
-        self.consumed[slot ^ 1] = tag - 1        # the previous frame's buffer (other slot) may now be overwritten
-        return self.frames[slot][:total], total
+        view, total = None, 0
+        if g == 0:
+            self._spin(lambda: all(self.done_tag[slot][h] >= tag for h in range(self.world)))
+            total = int(sum(int(self.lens[slot][h]) for h in range(self.world)))
+            view = self.frames[slot][:total]
+            self.released[0] = max(int(self.released[0]), tag - 2)    # frames up to j - 2 may be overwritten from now on
+        self.t_copy += t1 - t0
+        self.t_wait_done += time.perf_counter() - t1
+        self.k_col = j + 1
+        # Three frames in flight: start the next frame's copy now, so that it runs under the next submit and the
+        # kernels queued behind it (with fewer frames in flight this would only stall the caller).
+        if self.k_sub - self.k_issue >= 2:
+            self._issue(self.k_issue)
+        return view, total
 
     def close(self):
         if getattr(self, "_addr", None) is not None:
@@ -339,7 +359,7 @@ class HostAssembledRenderer:
             except Exception:
                 pass
             self._addr = None
-        self.lens = self.len_tag = self.done_tag = self.consumed = self.frames = None
+        self.lens = self.len_tag = self.done_tag = self.released = self.frames = None
         if getattr(self, "shm", None) is not None:
             try:
                 self.shm.close()

@@ -26,12 +26,9 @@ t0 = time.perf_counter()
 submit(0)
 for i in range(N):
     submit(i + 1)
-    if variant == "nocopy":
-        k = r.k_col; r.k_col += 1; r.done_ev[k & 1].synchronize()
-    else:
-        r.collect()
+    r.collect()
 t1 = time.perf_counter()
-r.collect() if variant != "nocopy" else None
+r.collect()
 torch.cuda.synchronize()
 print(variant, "wall per frame %.3f ms" % ((t1 - t0) * 1e3 / N))
 print("frame gpu ms:", ["%.3f" % ev[i][0].elapsed_time(ev[i][1]) for i in range(N)])

@@ -33,10 +33,13 @@ def _worker(rank, world, port, mode, x, y, n_frames, out_dir):
     r = multigpu.HostAssembledRenderer(ctx, dist, rank, world, x, y, mode)
     r.step(cams[0]); r.step(cams[0]); r.step(cams[0])          # free-running steps must not disturb submit/collect
     frames = []
-    r.submit(cams[0])
+    depth = 2 + (world % 2)                                    # two or three frames in flight
+    sub = 0
+    while sub < min(depth - 1, n_frames):
+        r.submit(cams[sub]); sub += 1
     for k in range(n_frames):
-        if k + 1 < n_frames:
-            r.submit(cams[k + 1])
+        if sub < n_frames:
+            r.submit(cams[sub]); sub += 1
         view, n = r.collect()
         if rank == 0:
             frames.append(view[:n].numpy().copy())
@@ -53,7 +56,7 @@ def test_host_assembled_frames_match_single_gpu(tmp_path, ctx, rtc, world, mode,
     import torch.multiprocessing as mp
     from rtc_b200 import scenes
     x, y = size
-    n_frames = 4
+    n_frames = 7
     mp.spawn(_worker, args=(world, _free_port(), mode, x, y, n_frames, str(tmp_path)), nprocs=world, join=True)
     got = np.load(tmp_path / "frames.npz")
     ctx.set_objects(scenes.config_scene("config2_1080p_64"))
