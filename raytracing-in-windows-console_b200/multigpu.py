@@ -43,23 +43,36 @@ def gather_planes(dist, rank, world, y, W, bpp, band_color, frame_color, band_gl
             w.wait()
 
 
-def weighted_bands(y, world, deficit_rows=0.0):
+def weighted_bands(y, world, deficit_rows=0.0, align=1, wave_units=0):
     """Bands for the case where rank 0 also runs the encoder: rank 0 gets `deficit_rows` fewer rows than the
     others (deficit = encode time / trace+shade time per row, measured), the remaining rows are split evenly.
-    Contiguous, exact cover of [0, y) for any y, world; deficit 0 reproduces bands()."""
+    `align` > 1 puts the boundaries on multiples of `align` rows (16 = the ray kernel's tile height: a band that ends
+    inside a tile row pays for the whole row, and one partial tile row too many can cost a whole extra tile wave).
+    `wave_units` > 0: the number of `align`-row units one tile wave of the ray kernel covers (SMs x warps per CTA /
+    tiles per row); if the deficit would push the other ranks just over one wave while everything fits into one wave
+    per rank, rank 0 takes the excess instead (a second wave costs more than the imbalance).
+    Contiguous, exact cover of [0, y) for any y, world; deficit 0 and align 1 reproduce bands()."""
     if world == 1:
         return [(0, y)]
     d = max(0.0, float(deficit_rows))
-    n0 = int(round((y + d) / world - d))
-    n0 = max(0, min(y, n0))
-    if d == 0.0:
+    if d == 0.0 and align <= 1:
         return bands(y, world)
-    out = [(0, n0)]
-    rest = y - n0
+    align = max(1, int(align))
+    units = (y + align - 1) // align                      # rows in units of `align`
+    du = d / align
+    n0 = int(round((units + du) / world - du))
+    n0 = max(0, min(units, n0))
+    if wave_units > 0 and units <= wave_units * world:
+        per_other = -(-(units - n0) // (world - 1))
+        if per_other > wave_units:
+            n0 = units - wave_units * (world - 1)
+    edges = [0, n0]
+    rest = units - n0
     for g in range(world - 1):
-        a, b = band(rest, g, world - 1)
-        out.append((n0 + a, n0 + b))
-    return out
+        edges.append(n0 + band(rest, g, world - 1)[1])
+    rows = [min(y, e * align) for e in edges]
+    rows[-1] = y
+    return [(rows[g], rows[g + 1]) for g in range(world)]
 
 
 class BandRenderer:
@@ -74,13 +87,15 @@ class BandRenderer:
     gather="nccl": bands are written locally and moved with batched NCCL send/recv.
     """
 
-    def __init__(self, ctx, dist, rank, world, x, y, mode, gather="ipc", deficit_rows=0.0):
+    def __init__(self, ctx, dist, rank, world, x, y, mode, gather="ipc", deficit_rows=0.0, align=16, wave_units=None):
         import torch
         from . import encode_capacity, mode_bpp, mode_has_glyph
         self.torch, self.ctx, self.dist, self.rank, self.world = torch, ctx, dist, rank, world
         self.x, self.y, self.W, self.mode, self.gather = x, y, x - 1, mode, gather
         self.bpp, self.gl = mode_bpp(mode), bool(mode_has_glyph(mode))
-        self.bands = weighted_bands(y, world, deficit_rows)
+        if wave_units is None:                     # 28 warps per SM, one 16x16-pixel tile per warp and wave
+            wave_units = (ctx.device_info()["sm_count"] * 28) // max(1, (x - 1 + 15) // 16) if align == 16 else 0
+        self.bands = weighted_bands(y, world, deficit_rows, align, wave_units)
         self.r0, self.r1 = self.bands[rank]
         self.cap = encode_capacity(x, y, mode)
         self.k = 0

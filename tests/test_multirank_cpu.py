@@ -84,3 +84,13 @@ def test_weighted_bands(rtc):
                     others = [b - a for a, b in bs[1:]]
                     assert bs[0][1] - bs[0][0] <= max(others) and max(others) - min(others) <= 1
     assert multigpu.weighted_bands(2160, 8, 62.0)[0] == (0, 216)
+    for y in (1, 7, 64, 270, 2160, 4321):
+        for world in (2, 3, 8):
+            for d in (0.0, 40.0, 62.0, 1e9):
+                bs = multigpu.weighted_bands(y, world, d, align=16)
+                assert len(bs) == world and bs[0][0] == 0 and bs[-1][1] == y
+                assert all(bs[i][1] == bs[i + 1][0] and bs[i][0] <= bs[i][1] for i in range(world - 1))
+                assert all(b[1] % 16 == 0 or b[1] == y for b in bs)
+    # 4K frame on 8 GPUs: 17 tile rows x 240 tiles fit one wave of 148 SMs x 28 warps, 18 do not -> rank 0 keeps 16
+    assert multigpu.weighted_bands(2160, 8, 62.0, align=16, wave_units=17) == [(0, 256)] + [(256 + 272 * g, 256 + 272 * (g + 1)) for g in range(7)]
+    assert multigpu.weighted_bands(2160, 8, 62.0, align=16)[0] == (0, 208)
