@@ -142,3 +142,50 @@ def test_update_objects_launch_limit(oracle):
     moved = oracle.update_objects(objs, 0.5, 0)
     assert moved.tobytes() != objs.tobytes()
     assert np.all(np.abs(moved["center"][:, 1]) <= 10.0)    # Sphere::Update clamps y into [-10,10]
+
+
+def test_encode_planes_equals_raw_minimiser_property(oracle):
+    """Property (hypothesis): for arbitrary colour / glyph / hit planes, the plane-based encoder the GPU is compared
+    against (orc_encode_planes: "emit the full cell iff the colour key differs from the previous traced cell") produces
+    exactly the bytes of the reference's own pipeline -- 20/12-byte cells laid out with row stride SIZE*x in the
+    20*x*y raw buffer (RayTracing.cu:585-608, :231-251), then the serial MinimizeRGB / Minimize8bit scan
+    (RayTracingManager.cu:251-319, :181-249) -- including its quirks: NUL-padded digits are bytes like any other, the
+    fg/bg selector and the glyph do not take part in the comparison, latestColor survives row ends."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=120, deadline=None)
+    @given(st.integers(2, 40), st.integers(1, 12), st.sampled_from([0, 1, 2, 3]), st.integers(0, 2 ** 32 - 1),
+           st.sampled_from([1, 2, 3, 255]))
+    def check(x, y, mode, seed, n_levels):
+        rng = np.random.default_rng(seed)
+        W = x - 1
+        bpp = 1 if mode in (0, 1) else 3
+        cs = mode_cell(mode)
+        has_glyph = mode in (0, 2)
+        levels = rng.integers(0, 256, n_levels).astype(np.uint8)
+        keys = levels[rng.integers(0, n_levels, (y * W, bpp))]
+        if has_glyph:                                              # ' ' == a miss (background selector), others == a hit
+            glyph = rng.choice(np.frombuffer(b"  .#@", np.uint8), y * W)
+        else:
+            glyph = None
+        raw = np.zeros(20 * x * y, np.uint8)
+        cell = ctypes.create_string_buffer(20)
+        for r in range(y):
+            for c in range(W):
+                i = r * W + c
+                g = int(glyph[i]) if has_glyph else 32
+                hit = 1 if (not has_glyph or g != 32) else 0
+                k = keys[i]
+                if has_glyph and not hit:                           # the reference's miss cell is black / index 16
+                    k = np.array([16], np.uint8) if bpp == 1 else np.zeros(3, np.uint8)
+                    keys[i] = k
+                col = (ctypes.c_uint8 * 3)(*[int(v) for v in (list(k) + [0, 0])[:3]])
+                n = oracle.L.orc_make_cell(mode, col, g, hit, cell)
+                assert n == cs
+                off = r * x * cs + c * cs
+                raw[off:off + cs] = np.frombuffer(cell.raw[:cs], np.uint8)
+        want = oracle.minimize(raw, x, y, mode)
+        got = oracle.encode_planes(keys.reshape(-1), glyph, x, y, mode)
+        assert np.array_equal(got, want)
+
+    check()
