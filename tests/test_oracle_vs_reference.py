@@ -20,7 +20,7 @@ def test_abi_sizes(reference):
 
 def test_frames_random(oracle, reference):
     rng = np.random.default_rng(42)
-    for trial in range(6):
+    for trial in range(120):
         n = int(rng.integers(1, 70))
         objs = scenes.random_spheres(n, 4242 + trial)
         if trial % 2:
