@@ -37,9 +37,12 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config3_4k_1024")
     ap.add_argument("--mode", default="RGB_PIXEL")
-    ap.add_argument("--gather", default="host", choices=["host", "nccl", "ipc"],
-                    help="N > 1: host = every rank encodes its band and copies its piece of the stream into one shared pinned "
-                         "host frame (no data-path collective); ipc / nccl = planes gathered to GPU 0 over NVLink, encoded there")
+    ap.add_argument("--gather", default="host", choices=["host", "p2p"],
+                    help="N > 1: host = every device encodes its band and copies its piece of the stream into one pinned host "
+                         "frame (no data-path collective); p2p = bands stored straight into GPU 0's planes over NVLink, encoded there. "
+                         "The other mode is measured too and reported as a sub-record.")
+    ap.add_argument("--headline-only", action="store_true", help="skip the sub-records (culling, other gather, config 4, config 2 + shadows, baselines)")
+    ap.add_argument("--no-config4", action="store_true")
     ap.add_argument("--orbit", type=int, default=0, help="camera orbit of this many frames (config 4: 120); 0 = fixed camera")
     ap.add_argument("--cull", action="store_true", help="per-tile sphere culling on (identical results, fewer tests executed)")
     ap.add_argument("--shadows", action="store_true", help="shadow-ray extension on (second, light-origin trace pass)")
@@ -60,9 +63,10 @@ def cpu_model():
 
 def ncu_traffic():
     """DRAM bytes per launch of our kernels from the committed ncu --set full captures (profiles/)."""
-    path = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    import glob
+    paths = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic.json")))     # the latest round's captures
     try:
-        return json.load(open(path))
+        return json.load(open(paths[-1]))
     except Exception:
         return {}
 
@@ -116,14 +120,14 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_sample(name, mode, seconds, threads=None):
+def cpu_reference_sample(name, mode, seconds, threads=None, camera_fn=None):
     """Time the reference's own CPU code (oracle/_ref, built from the unmodified sources) on a
     bounded sample of the workload: a window of 16-row block rows of the frame, all host threads.
     Falls back to the restated oracle (kind 'port') where oracle/_ref is absent."""
     from oracle.oracle import Oracle, Reference
     from rtc_b200 import scenes
     objs = scenes.config_scene(name)
-    p = scenes.config_camera(name)
+    p = scenes.config_camera(name, camera_fn=camera_fn)
     threads = threads or os.cpu_count() or 1
     n_obj = len(objs)
     gy = (p.y + 15) // 16
@@ -215,19 +219,22 @@ def ref_cuda_sample(name, mode, frames=3):
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation on the host cores."""
+    """--impl reference: the reference's own CPU implementation on the host cores.  Nothing of the product is loaded
+    here: the camera block comes from the oracle's restatement of Camera3D (orc_camera_params), not from librtc_b200."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import rtc_b200
-    mode = rtc_b200.MODE_NAMES.index(args.mode)
-    from rtc_b200 import scenes
-    p = scenes.config_camera(args.workload)
+    from rtc_b200 import _types, scenes                        # numpy / ctypes PODs only; does not dlopen the library
+    from oracle.oracle import Oracle
+    orc = Oracle()
+    mode = _types.MODE_NAMES.index(args.mode)
+    p = scenes.config_camera(args.workload, camera_fn=orc.camera_params)
+    objs = scenes.config_scene(args.workload)
     per_step = max(1.0, min(args.cpu_seconds, 150.0 / max(1, args.steps + args.warmup)))
     vals = []
     last = None
     for i in range(args.warmup + args.steps):
-        last = cpu_reference_sample(args.workload, mode, per_step)
+        last = cpu_reference_sample(args.workload, mode, per_step, camera_fn=orc.camera_params)
         if i >= args.warmup:
             vals.append(last)
     rays = sum(v["rays"] for v in vals)
@@ -238,7 +245,11 @@ def run_reference(args):
         "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * frame_rays / (value * 1e6),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "mode": args.mode, "note": "ms_per_step = whole-frame time extrapolated from the sample rate"},
+        "config": {"workload": args.workload, "x": p.x, "y": p.y, "rays_per_frame": frame_rays,
+                   "spheres": int((objs["type"] == 2).sum()), "objects": int(len(objs)), "mode": args.mode,
+                   "parallelism": "host threads", "gather": None, "driver": "reference RayTrace_* kernels compiled for CPU (oracle/_ref)",
+                   "devices": [], "bands": [[0, p.y]], "camera_orbit_frames": args.orbit, "shadow_rays": False, "sphere_culling": False,
+                   "l2": "n/a", "note": "ms_per_step = whole-frame time extrapolated from the sample rate"},
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": last["cores"], "kind": last["kind"], "sample": last["sample"],
                          "cpu_model": cpu_model()},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -249,270 +260,250 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def sha16(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def measure_ctx(ctx, torch, stream, flush, objs, cams, mode, flags, steps, warmup, e2e_steps=None):
+    """One GPU through rtc_ctx.  Device-timed frames (CUDA events on the launching stream, L2 flushed between steps)
+    and the end-to-end loop through rtc_scene_set_objects + rtc_submit / rtc_collect with host buffers."""
+    import rtc_b200
+    k = [0]
+
+    def cam():
+        c = cams[k[0] % len(cams)]
+        k[0] += 1
+        return c
+    ctx.set_objects(objs)
+    for _ in range(max(3, warmup)):
+        ctx.render(cam(), mode, flags)
+    torch.cuda.synchronize()
+    stage = {"prep_ms": 0.0, "trace_ms": 0.0, "shade_ms": 0.0, "encode_ms": 0.0}
+    total_ms, launches, t = 0.0, 0, None
+    for _ in range(steps):
+        flush.zero_()                              # evict L2 between timed iterations (untimed)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        ctx.render(cam(), mode, flags)
+        b.record(stream)
+        torch.cuda.synchronize()
+        total_ms += a.elapsed_time(b)
+        t = ctx.timings()
+        for kk in stage:
+            stage[kk] += t[kk]
+        launches = t["launches"]
+    res = {"ms_per_step": total_ms / steps, "stages_ms": {kk: v / steps for kk, v in stage.items()}, "launches_per_step": launches,
+           "sphere_tests": t["sphere_tests"]}
+    # ---- end to end: every step uploads the scene + camera block from host memory and brings that step's stream
+    # back to pinned host memory; the D2H of frame k overlaps the kernels of frame k+1 (rtc_submit / rtc_collect)
+    n = e2e_steps or steps
+    upd = rtc_b200.FLAG_UPDATE_REF_LAUNCH_LIMIT | flags
+    for _ in range(2):
+        ctx.set_objects(objs)
+        ctx.update(cam(), mode, dt=0.0, flags=upd)
+    torch.cuda.synchronize()
+    ctx.set_objects(objs)
+    ctx.submit(cam(), mode, 0.0, upd)
+    t0 = time.perf_counter()
+    nbytes = 0
+    for _ in range(n):
+        ctx.set_objects(objs)
+        ctx.submit(cam(), mode, 0.0, upd)          # frame k+1
+        nbytes = len(ctx.collect())                # frame k: stream in pinned host memory
+    t1 = time.perf_counter()
+    ctx.collect()
+    res["e2e_ms"] = (t1 - t0) * 1e3 / n
+    res["d2h_bytes"] = int(nbytes + 8)
+    res["h2d_bytes"] = int(objs.nbytes + 96)
+    t2 = time.perf_counter()
+    for _ in range(n):
+        ctx.set_objects(objs)
+        ctx.update(cam(), mode, dt=0.0, flags=upd)
+    res["sync_ms"] = (time.perf_counter() - t2) * 1e3 / n
+    return res
+
+
+def measure_mgpu(m, objs, cams, mode, flags, steps, warmup, e2e_steps=None):
+    """N GPUs through rtc_mgpu (one process, row bands).  `value`: per step every device's L2 is flushed (untimed), the
+    frame is submitted and collected; the step's time is what the CUDA events on each device's stream say (first kernel
+    to end of that device's last kernel; in the p2p gather device 0's last kernel is the encode of the assembled frame);
+    summed per device, maximum over devices.  `e2e`: wall clock of the pipelined loop, scene + camera uploaded from host
+    memory every frame, the assembled stream back in one pinned host buffer every frame."""
+    import rtc_b200
+    k = [0]
+
+    def cam():
+        c = cams[k[0] % len(cams)]
+        k[0] += 1
+        return c
+    upd = rtc_b200.FLAG_UPDATE_REF_LAUNCH_LIMIT | flags
+    m.set_objects(objs)
+    for _ in range(max(3, warmup)):
+        m.update(cam(), mode, 0.0, upd)
+    per_dev = np.zeros(m.n)
+    enc = 0.0
+    info = None
+    for _ in range(steps):
+        m.flush_l2()
+        m.update(cam(), mode, 0.0, upd)
+        info = m.last_frame()
+        per_dev += np.array(info["device_ms"])
+        enc += info["encode_ms"]
+    res = {"ms_per_step": float(per_dev.max()) / steps, "per_device_ms": [float(v) / steps for v in per_dev], "bands": info["bands"],
+           "encode_ms_on_gpu0": enc / steps}
+    n = e2e_steps or steps
+    m.set_objects(objs)
+    m.submit(cam(), mode, 0.0, upd)
+    m.set_objects(objs)
+    m.submit(cam(), mode, 0.0, upd)
+    t0 = time.perf_counter()
+    nbytes = 0
+    for _ in range(n):
+        m.set_objects(objs)                        # scene + camera block from host memory every frame
+        m.submit(cam(), mode, 0.0, upd)            # frame k+2
+        nbytes = len(m.collect())                  # frame k: the assembled stream in pinned host memory
+    t1 = time.perf_counter()
+    m.collect(); m.collect()
+    res["e2e_ms"] = (t1 - t0) * 1e3 / n
+    res["d2h_bytes"] = int(nbytes + 8 * m.n)
+    res["h2d_bytes"] = int(objs.nbytes + 96) * m.n
+    t2 = time.perf_counter()
+    for _ in range(max(3, n // 4)):
+        m.set_objects(objs)
+        m.update(cam(), mode, 0.0, upd)
+    res["sync_ms"] = (time.perf_counter() - t2) * 1e3 / max(3, n // 4)
+    return res
+
+
+def parity_streams(ctx1, objs, cams, mode, flags):
+    """Single-GPU streams (rtc_update on one context) of a few cameras: the yardstick of the N-GPU parity check."""
+    import rtc_b200
+    ctx1.set_objects(objs)
+    return [sha16(ctx1.update(c, mode, dt=0.0, flags=flags | rtc_b200.FLAG_UPDATE_REF_LAUNCH_LIMIT)) for c in cams]
+
+
+def parity_mgpu(m, objs, cams, mode, flags):
+    import rtc_b200
+    m.set_objects(objs)
+    return [sha16(m.update(c, mode, 0.0, flags | rtc_b200.FLAG_UPDATE_REF_LAUNCH_LIMIT)) for c in cams]
+
+
 def run_ours(args):
     import torch
     import rtc_b200
-    from rtc_b200 import multigpu, scenes
+    from rtc_b200 import scenes
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    N = args.gpus
     torch.cuda.set_device(local_rank)
-    dist = None
+    dist, gloo = None, None
     if world > 1:
+        # One rank per GPU is the launch contract; the FRAME PATH is one process: rank 0 drives all N devices through
+        # the library's multi-GPU driver (rtc_mgpu: a worker thread + stream per device).  NCCL carries the rank check
+        # (a barrier over all N ranks on their GPUs) and the timing reduction; the other ranks then wait on a gloo
+        # barrier (host-side, so that nothing of theirs spins on the GPUs rank 0 is timing).
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        gloo = dist.new_group(backend="gloo")
+        dist.barrier()
+        torch.cuda.synchronize()
+        if rank != 0:
+            dist.barrier(group=gloo)                            # rank 0 has finished measuring
+            tt = torch.zeros(2, dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.destroy_process_group()
+            return
 
     mode = rtc_b200.MODE_NAMES.index(args.mode)
     name = args.workload
     objs = scenes.config_scene(name)
     p = scenes.config_camera(name)
-    # --orbit N: frame i is seen from camera i mod N of an N-frame orbit about the scene centre
     cams = [scenes.config_camera(name, frame=k, n_frames=args.orbit) for k in range(args.orbit)] if args.orbit > 0 else [p]
-    frame_no = [0]
     rflags = (rtc_b200.FLAG_SHADOWS if args.shadows else 0) | (rtc_b200.FLAG_CULL if args.cull else 0)
-
-    def next_cam():
-        c = cams[frame_no[0] % len(cams)]
-        frame_no[0] += 1
-        return c
     x, y = p.x, p.y
     W = x - 1
     bpp = rtc_b200.mode_bpp(mode)
-    has_glyph = rtc_b200.mode_has_glyph(mode)
     n_spheres = int((objs["type"] == 2).sum())
     frame_rays = W * y
+    n_vis = torch.cuda.device_count()
+    devices = list(range(N)) if n_vis >= N else [g % n_vis for g in range(N)]     # fewer GPUs visible: bands share devices (dev boxes)
 
-    ctx = rtc_b200.Context(local_rank)            # raises without a GPU: no CPU fallback
-    stream = torch.cuda.Stream()                  # one explicit stream for torch, NCCL and the rtc kernels
+    ctx = rtc_b200.Context(devices[0])            # raises without a GPU: no CPU fallback
+    stream = torch.cuda.Stream()                  # one explicit stream for torch and the rtc kernels
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
-    ctx.set_objects(objs)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")      # > 126 MB L2
 
-    cap = rtc_b200.encode_capacity(x, y, mode)
-    launches_per_step = 0
-    renderer = None
-    deficit = 0.0
-    if world == 1:
-        def step():
-            ctx.render(next_cam(), mode, rflags)
+    sampler = ClockSampler(devices[0])
+    sampler.start()
+    m = None
+    if N == 1:
+        r = measure_ctx(ctx, torch, stream, flush, objs, cams, mode, rflags, args.steps, args.warmup)
     else:
-        # Row bands: every rank traces + shades its band straight into (ipc) or followed by NCCL send/recv into (nccl)
-        # rank 0's frame planes; rank 0 encodes the assembled frame.  Rank 0 also pays for the encoder, so it gets a
-        # smaller band: the deficit (in rows) is measured on rank 0 from one whole frame's stage timings.
-        if args.gather == "host":
-            # needs a POSIX shared-memory segment that can be page-locked; if any rank cannot have it, every rank
-            # falls back to gathering the planes on GPU 0 over NVLink
-            try:                                   # collective: raises on every rank or on none
-                renderer = multigpu.HostAssembledRenderer(ctx, dist, rank, world, x, y, mode)
-            except RuntimeError as e:
-                sys.stderr.write("rank %d: %s -- falling back to --gather ipc\n" % (rank, e))
-                renderer = None
-                args.gather = "ipc"
-        if renderer is None:
-            hdr = [0.0]
-            if rank == 0:
-                for _ in range(3):
-                    ctx.render(p, mode)
-                torch.cuda.synchronize()
-                t = ctx.timings()
-                hdr = [t["encode_ms"] / max(1e-9, (t["trace_ms"] + t["shade_ms"]) / y)]
-            dist.broadcast_object_list(hdr, src=0)
-            deficit = float(hdr[0])
-            renderer = multigpu.BandRenderer(ctx, dist, rank, world, x, y, mode, gather=args.gather, deficit_rows=deficit)
-
-        def step():
-            return renderer.step(next_cam(), rflags)
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    # ---- device-timed throughput ---------------------------------------------------------------
-    for _ in range(max(3, args.warmup)):
-        step()
-    sync_all()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    stage = {"prep_ms": 0.0, "trace_ms": 0.0, "shade_ms": 0.0, "encode_ms": 0.0}
-    sync_all()
-    for i in range(args.steps):
-        flush.zero_()                              # evict L2 between timed iterations (untimed)
-        ev[i][0].record(stream)
-        step()
-        ev[i][1].record(stream)
-        if world == 1:
-            torch.cuda.synchronize()
-            t = ctx.timings()
-            for k in stage:
-                stage[k] += t[k]
-            launches_per_step = t["launches"]
-    sync_all()
-    clocks = sampler.stop() if rank == 0 else None
-    my_ms = sum(a.elapsed_time(b) for a, b in ev)
+        gather = rtc_b200.GATHER_P2P if args.gather == "p2p" else rtc_b200.GATHER_HOST
+        m = rtc_b200.MultiGpu(devices, gather)
+        r = measure_mgpu(m, objs, cams, mode, rflags, args.steps, args.warmup)
+    clocks = sampler.stop()
+    ms_per_step = r["ms_per_step"]
     if dist is not None:
-        tt = torch.tensor([my_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        total_ms = float(tt.item())
-    else:
-        total_ms = my_ms
-    ms_per_step = total_ms / args.steps
+        dist.barrier(group=gloo)
+        tt = torch.tensor([ms_per_step, r["e2e_ms"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)                # max over ranks (the other ranks time nothing: 0)
+        ms_per_step = float(tt[0].item())
     value = frame_rays / (ms_per_step * 1e-3) / 1e6
 
-    # ---- end to end through the C-ABI with host buffers (N == 1 path; N > 1: rank 0 reads the stream back)
-    e2e = None
-    if world == 1:
-        # Pipelined public API (rtc_submit / rtc_collect, the asynchronous form of RayTracingManager::Update): every
-        # step uploads the scene + camera block from (pinned-staged) host memory and brings that step's stream back
-        # to pinned host memory; the D2H of frame k overlaps the kernels of frame k+1.
-        upd_flags = rtc_b200.FLAG_UPDATE_REF_LAUNCH_LIMIT | rflags
-        for _ in range(2):
-            ctx.set_objects(objs)
-            s = ctx.update(p, mode, dt=0.0, flags=upd_flags)
-        torch.cuda.synchronize()
-        ctx.set_objects(objs)
-        ctx.submit(p, mode, 0.0, upd_flags)
-        t0 = time.perf_counter()
-        nbytes = 0
-        for _ in range(args.steps):
-            ctx.set_objects(objs)                  # scene + camera block from host memory every frame
-            ctx.submit(next_cam(), mode, 0.0, upd_flags)    # frame k+1
-            s = ctx.collect()                      # frame k: stream in pinned host memory
-            nbytes = len(s)
-        t1 = time.perf_counter()
-        ctx.collect()
-        dev_ms_in_pipeline = ctx.timings()["total_ms"]
-        e2e_ms = (t1 - t0) * 1e3 / args.steps
-        # the synchronous form (one rtc_update per frame, as the reference's Update), for comparison
-        t2 = time.perf_counter()
-        for _ in range(args.steps):
-            ctx.set_objects(objs)
-            s = ctx.update(p, mode, dt=0.0, flags=upd_flags)
-        t3 = time.perf_counter()
-        sync_ms = (t3 - t2) * 1e3 / args.steps
-        e2e = {"value": frame_rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": int(objs.nbytes + 96), "d2h_bytes_per_step": int(nbytes + 8),
-               "api": "rtc_scene_set_objects + rtc_submit / rtc_collect (pipelined RayTracingManager::Update), stream returned in pinned host memory",
-               "device_ms_of_last_pipelined_frame": dev_ms_in_pipeline,
-               "synchronous_rtc_update": {"value": frame_rays / (sync_ms * 1e-3) / 1e6, "ms_per_step": sync_ms}}
-    else:
-        # Pipelined like rtc_submit / rtc_collect: frame k+1 is enqueued on every rank before rank 0 waits for frame k's
-        # stream length and copies the stream to pinned host memory on a separate copy stream.
-        host = ([torch.empty(cap, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
-                if (rank == 0 and args.gather != "host") else None)
-        copy_stream = torch.cuda.Stream()
-        done = [torch.cuda.Event(), torch.cuda.Event()]
-        h_total = torch.zeros(2, dtype=torch.int64, pin_memory=True) if rank == 0 else None
+    def mr(ms, rays=frame_rays):
+        return rays / (ms * 1e-3) / 1e6
 
-        def submit():
-            ctx.set_objects(objs)
-            sl = renderer.step(next_cam(), rflags)
-            if rank == 0:
-                h_total[sl:sl + 1].copy_(renderer.total[sl:sl + 1], non_blocking=True)
-                done[sl].record(stream)
-            return sl
-
-        def collect(sl):
-            if rank != 0:
-                return 0
-            done[sl].synchronize()
-            n = int(h_total[sl])
-            with torch.cuda.stream(copy_stream):
-                host[sl][:n].copy_(renderer.out[sl][:n], non_blocking=True)
-            copy_stream.synchronize()
-            return n
-
-        if args.gather == "host":
-            def submit():                                  # noqa: F811
-                ctx.set_objects(objs)
-                return renderer.submit(next_cam(), rflags)
-
-            def collect(sl):                               # noqa: F811
-                return renderer.collect()[1]
-        sync_all()
-        if args.gather == "host":
-            # three frames in flight: the copy of frame k+1 is issued while frame k is returned
-            submit(); submit()
-            t0 = time.perf_counter()
-            nbytes = 0
-            for _ in range(args.steps):
-                submit()
-                nbytes = collect(None)
-            t1 = time.perf_counter()
-            collect(None); collect(None)
-        else:
-            prev = submit()
-            t0 = time.perf_counter()
-            nbytes = 0
-            for _ in range(args.steps):
-                cur = submit()
-                nbytes = collect(prev)
-                prev = cur
-            t1 = time.perf_counter()
-            collect(prev)
-        sync_all()
-        tt = torch.tensor([(t1 - t0) * 1e3 / args.steps], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_ms = float(tt.item())
-        host_breakdown = None
-        if args.gather == "host":
-            kk = max(1, renderer.k_col)
-            host_breakdown = {"wait_gpu_ms": renderer.t_wait_gpu * 1e3 / kk, "wait_lengths_ms": renderer.t_wait_len * 1e3 / kk,
-                              "wait_copy_ms": renderer.t_copy * 1e3 / kk, "wait_ranks_ms": renderer.t_wait_done * 1e3 / kk,
-                              "submit_ms": renderer.t_submit * 1e3 / kk}
-        e2e = {"rank0_collect_breakdown": host_breakdown,"value": frame_rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": int(objs.nbytes + 96) * world, "d2h_bytes_per_step": int(nbytes + 8),
-               "api": ("per rank rtc_scene_set_objects + rtc_trace_band + rtc_encode_band, every rank copies its piece of the stream into one shared pinned host frame (pipelined three deep)"
-                       if args.gather == "host" else
-                       "per rank rtc_scene_set_objects + rtc_trace_band, bands gathered to GPU 0, rtc_encode, stream copied to pinned host memory (pipelined two deep)")}
-
-    if rank != 0:
-        if renderer is not None:
-            renderer.close()
-        if dist is not None:
-            dist.destroy_process_group()
-        return
+    e2e = {"value": mr(r["e2e_ms"]), "unit": "Mrays/s", "ms_per_step": r["e2e_ms"], "h2d_bytes_per_step": r["h2d_bytes"],
+           "d2h_bytes_per_step": r["d2h_bytes"],
+           "api": ("rtc_scene_set_objects + rtc_submit / rtc_collect (pipelined RayTracingManager::Update), stream returned in pinned host memory"
+                   if N == 1 else
+                   "rtc_mgpu_scene_set_objects + rtc_mgpu_submit / rtc_mgpu_collect (RayTracingManager::Update across %d GPUs, one process, "
+                   "three frames in flight), the assembled stream returned in one pinned host buffer" % N),
+           "synchronous_update": {"value": mr(r["sync_ms"]), "ms_per_step": r["sync_ms"]}}
 
     pk = peaks()
     sm_count = ctx.device_info()["sm_count"]
     fp32_peak = sm_count * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12          # TFLOP/s at the max SM clock
     line = {
-        "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": N, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": name, "x": x, "y": y, "rays_per_frame": frame_rays, "spheres": n_spheres,
-                   "objects": int(len(objs)), "mode": args.mode, "parallelism": "rowband%d" % world,
-                   "gather": args.gather if world > 1 else None,
-                   "bands": renderer.bands if renderer is not None else [[0, y]], "camera_orbit_frames": args.orbit, "shadow_rays": bool(args.shadows), "sphere_culling": bool(args.cull),
-                   "l2": "flushed between timed steps (256 MiB memset, untimed)"},
+                   "objects": int(len(objs)), "mode": args.mode, "parallelism": "rowband%d" % N,
+                   "gather": args.gather if N > 1 else None, "driver": "rtc_ctx" if N == 1 else "rtc_mgpu (one process, worker thread per device)",
+                   "devices": devices, "bands": r.get("bands", [[0, y]]), "camera_orbit_frames": args.orbit,
+                   "shadow_rays": bool(args.shadows), "sphere_culling": bool(args.cull),
+                   "l2": "flushed between timed steps (256 MiB memset per device, untimed)"},
         "frames_per_s": 1e3 / ms_per_step,
         "clocks": clocks, "e2e": e2e,
     }
-    if world == 1:
-        trace_ms = stage["trace_ms"] / args.steps
-        enc_ms = stage["encode_ms"] / args.steps
+    traffic = ncu_traffic()
+    if N == 1:
+        trace_ms = r["stages_ms"]["trace_ms"]
+        enc_ms = r["stages_ms"]["encode_ms"]
         n_passes = 2 if args.shadows else 1                    # the shadow pass runs the same packed test over every tile with a shaded pixel
-        tests_executed = ctx.timings()["sphere_tests"]         # of the last frame (tile-granular: >= rays x spheres per pass)
-        # FLOPs of the tests actually executed: rays x spheres per pass without culling, fewer with --cull
+        tests_executed = r["sphere_tests"]                     # of the last frame (tile-granular: >= rays x spheres per pass)
         achieved = 7.0 * (tests_executed if args.cull else frame_rays * n_spheres * n_passes) / (trace_ms * 1e-3) / 1e12
         try:
             measured_ffma = max(ctx.fp32_peak(0, 3000)[0] for _ in range(2))
             measured_ffma2 = max(ctx.fp32_peak(1, 3000)[0] for _ in range(2))
         except Exception:
             measured_ffma = measured_ffma2 = None
+        ctx.render(p, mode, rflags)
         _, n_stream = ctx.frame_ansi_device()
-        line["roofline"] = {"bound": "fp32", "kernel": "trace_kernel", "achieved": achieved, "peak": fp32_peak,
-                            "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                            "traffic": (ncu_traffic().get("trace_kernel", {}).get("traffic") if name == "config3_4k_1024" else None),
-                            "traffic_note": "DRAM bytes per launch from profiles/r01_ncu_traffic.json (ncu --set full): the kernel is FP32-pipe bound, 0.1 % of HBM bandwidth",
+        tk = traffic.get("trace_kernel", {})
+        line["roofline"] = {"bound": "fp32", "kernel": "trace_kernel (ray generation + nearest hit + shade/quantise epilogue, one launch)",
+                            "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+                            "traffic": tk.get("traffic") if name == tk.get("workload") else None,
+                            "traffic_source": tk.get("source"),
                             "peak_source": "%d SMs x 128 lanes x 2 FLOP x %.0f MHz (%s sm_max_mhz); not in MEASURED_PEAKS.json, which has HBM and bf16 tensor only"
                                            % (sm_count, pk["sm_max_mhz"], pk["source"]),
                             "algorithmic_flops_per_launch": 7.0 * frame_rays * n_spheres, "launches_in_kernel_ms": n_passes, "kernel_ms": trace_ms,
@@ -528,7 +519,8 @@ def run_ours(args):
             line["roofline_encoder"] = {"bound": "hbm", "kernel": "count_kernel + emit_kernel (2 launches)",
                                         "workload": "config5_encode_8k: 7681x4320, i.i.d. random RGB",
                                         "achieved": st_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": st_gbs / pk["hbm_gbs"],
-                                        "traffic": sum(ncu_traffic().get(k, {}).get("traffic", 0.0) for k in ("count_kernel<3>", "emit_kernel<3, 0>")) or None,
+                                        "traffic": sum(traffic.get(k, {}).get("traffic", 0.0) for k in ("count_kernel<3>", "emit_kernel<3, 0>")) or None,
+                                        "traffic_source": traffic.get("emit_kernel<3, 0>", {}).get("source"),
                                         "algorithmic_bytes_per_launch": st_in + st_out, "kernel_ms": st_ms,
                                         "peak_source": pk["source"] + " (MEASURED_PEAKS.json hbm_gbs)"}
         except Exception as e:
@@ -536,39 +528,84 @@ def run_ours(args):
         line["encoder_on_rendered_frame"] = {"workload": name, "algorithmic_bytes": enc_bytes, "kernel_ms": enc_ms,
                                              "achieved_gbs": enc_bytes / (enc_ms * 1e-3) / 1e9,
                                              "cells_per_ns": frame_rays / (enc_ms * 1e6)}
-        line["stages_ms"] = {k: v / args.steps for k, v in stage.items()}
+        line["stages_ms"] = r["stages_ms"]
+        line["gpu_launches"] = int(r["launches_per_step"] * args.steps)
+    else:
+        line["per_device_ms"] = r["per_device_ms"]
+        line["encode_ms_on_gpu0"] = r["encode_ms_on_gpu0"]
+        # hoist + trace(+shade epilogue) + count + emit per device (host gather) or hoist + trace per device and count + emit on GPU 0 (p2p)
+        line["gpu_launches"] = int((4 * N if args.gather == "host" else 2 * N + 2) * args.steps)
+
+    if not args.headline_only:
+        sub_steps = max(8, min(args.steps, 40))
+        # ---- the same frames with per-tile sphere culling (RTC_FLAG_CULL): identical output, fewer tests executed --
         if not args.cull:
-            # The same frames with per-tile sphere culling (RTC_FLAG_CULL): identical output (tests/test_gpu_parity.py::
-            # test_culling_is_invisible), fewer ray-sphere tests executed -- reported beside the brute-force headline
-            # because it changes the FLOP accounting the roofline above is defined on.
             try:
-                cflags = rflags | rtc_b200.FLAG_CULL
-                for _ in range(3):
-                    ctx.render(next_cam(), mode, cflags)
-                torch.cuda.synchronize()
-                k = max(10, min(args.steps, 50))
-                cms, cst = 0.0, {"trace_ms": 0.0, "shade_ms": 0.0, "encode_ms": 0.0}
-                for _ in range(k):
-                    flush.zero_()
-                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    a.record(stream)
-                    ctx.render(next_cam(), mode, cflags)
-                    b.record(stream)
-                    torch.cuda.synchronize()
-                    cms += a.elapsed_time(b)
-                    t = ctx.timings()
-                    for kk in cst:
-                        cst[kk] += t[kk]
-                cms /= k
-                line["with_culling"] = {"value": frame_rays / (cms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": cms,
-                                        "frames_per_s": 1e3 / cms, "stages_ms": {kk: v / k for kk, v in cst.items()},
-                                        "sphere_tests_executed": t["sphere_tests"],
-                                        "fraction_of_brute_force_tests": t["sphere_tests"] / max(1, frame_rays * n_spheres * n_passes),
-                                        "output": "bit-identical to the brute-force frame"}
+                cf = rflags | rtc_b200.FLAG_CULL
+                rc = (measure_ctx(ctx, torch, stream, flush, objs, cams, mode, cf, sub_steps, 3) if N == 1 else
+                      measure_mgpu(m, objs, cams, mode, cf, sub_steps, 3))
+                line["with_culling"] = {"value": mr(rc["ms_per_step"]), "unit": "Mrays/s", "ms_per_step": rc["ms_per_step"],
+                                        "e2e": {"value": mr(rc["e2e_ms"]), "ms_per_step": rc["e2e_ms"]},
+                                        "stages_ms": rc.get("stages_ms"), "sphere_tests_executed": rc.get("sphere_tests"),
+                                        "output": "bit-identical to the brute-force frame (tests/test_gpu_parity.py::test_culling_is_invisible)"}
             except Exception as e:
                 line["with_culling"] = {"error": repr(e)}
-        line["gpu_launches"] = int(launches_per_step * args.steps)
-        if not args.no_cpu_baseline:
+        # ---- N > 1: the other gather, and the N-GPU bytes against a single-GPU frame (outside every timed region) ----
+        parity = {}
+        if N > 1:
+            other = "p2p" if args.gather == "host" else "host"
+            try:
+                want = parity_streams(ctx, objs, cams[:3], mode, rflags)
+                parity[args.gather] = parity_mgpu(m, objs, cams[:3], mode, rflags) == want
+                m2 = rtc_b200.MultiGpu(devices, rtc_b200.GATHER_P2P if other == "p2p" else rtc_b200.GATHER_HOST)
+                ro = measure_mgpu(m2, objs, cams, mode, rflags, sub_steps, 3)
+                parity[other] = parity_mgpu(m2, objs, cams[:3], mode, rflags) == want
+                m2.close()
+                line["gather_" + other] = {"value": mr(ro["ms_per_step"]), "unit": "Mrays/s", "ms_per_step": ro["ms_per_step"],
+                                           "e2e": {"value": mr(ro["e2e_ms"]), "ms_per_step": ro["e2e_ms"]}, "bands": ro["bands"],
+                                           "per_device_ms": ro["per_device_ms"], "encode_ms_on_gpu0": ro["encode_ms_on_gpu0"]}
+            except Exception as e:
+                line["gather_" + other] = {"error": repr(e)}
+                parity[other] = False
+        # ---- config 4 (7681x4320, 4096 spheres, camera orbit: the configuration the >= 7x scaling target is stated on)
+        if name != "config4_8k_4096" and not args.no_config4:
+            try:
+                o4 = scenes.config_scene("config4_8k_4096")
+                n_orbit = 24
+                c4 = [scenes.config_camera("config4_8k_4096", frame=k * 5, n_frames=120) for k in range(n_orbit)]   # every 5th of the 120 orbit frames
+                rays4 = (c4[0].x - 1) * c4[0].y
+                if N == 1:
+                    r4 = measure_ctx(ctx, torch, stream, flush, o4, c4, rtc_b200.RGB_PIXEL, 0, n_orbit, 3, e2e_steps=n_orbit)
+                else:
+                    r4 = measure_mgpu(m, o4, c4, rtc_b200.RGB_PIXEL, 0, n_orbit, 3, e2e_steps=n_orbit)
+                    want4 = parity_streams(ctx, o4, c4[:2], rtc_b200.RGB_PIXEL, 0)
+                    parity["config4_" + args.gather] = parity_mgpu(m, o4, c4[:2], rtc_b200.RGB_PIXEL, 0) == want4
+                line["config4_orbit"] = {"workload": "config4_8k_4096: 7681x4320, 4096 spheres, 24 frames of the 120-frame orbit (every 5th)",
+                                         "value": mr(r4["ms_per_step"], rays4), "unit": "Mrays/s", "ms_per_step": r4["ms_per_step"],
+                                         "frames_per_s": 1e3 / r4["ms_per_step"], "steps": n_orbit,
+                                         "e2e": {"value": mr(r4["e2e_ms"], rays4), "ms_per_step": r4["e2e_ms"], "frames_per_s": 1e3 / r4["e2e_ms"],
+                                                 "d2h_bytes_per_step": r4["d2h_bytes"], "h2d_bytes_per_step": r4["h2d_bytes"]},
+                                         "bands": r4.get("bands", [[0, c4[0].y]]), "per_device_ms": r4.get("per_device_ms"),
+                                         "stages_ms": r4.get("stages_ms"),
+                                         "roofline_frac": (7.0 * rays4 * 4096 / (r4["stages_ms"]["trace_ms"] * 1e-3) / 1e12 / fp32_peak) if N == 1 else None}
+            except Exception as e:
+                line["config4_orbit"] = {"error": repr(e)}
+        if N > 1:
+            line["parity_check"] = {"n_gpu_equals_1_gpu": bool(parity) and all(parity.values()), "cases": parity,
+                                    "how": "sha256 of the assembled N-GPU stream (rtc_mgpu_update) == sha256 of rtc_update on one context, same cameras; outside the timed regions"}
+        # ---- config 2 with shadow rays (1921x1080, 64 spheres + plane, primary + shadow rays) on one GPU --------------
+        if N == 1 and not args.shadows:
+            try:
+                o2 = scenes.config_scene("config2_1080p_64")
+                c2 = [scenes.config_camera("config2_1080p_64")]
+                rays2 = (c2[0].x - 1) * c2[0].y
+                r2 = measure_ctx(ctx, torch, stream, flush, o2, c2, rtc_b200.RGB_PIXEL, rtc_b200.FLAG_SHADOWS, sub_steps, 3)
+                line["config2_shadows"] = {"workload": "config2_1080p_64: 1921x1080, 64 spheres + plane, primary + shadow rays (RTC_FLAG_SHADOWS: an extension, the reference casts none)",
+                                           "value": mr(r2["ms_per_step"], rays2), "unit": "Mrays/s (primary rays)", "ms_per_step": r2["ms_per_step"],
+                                           "e2e": {"value": mr(r2["e2e_ms"], rays2), "ms_per_step": r2["e2e_ms"]}, "stages_ms": r2["stages_ms"]}
+            except Exception as e:
+                line["config2_shadows"] = {"error": repr(e)}
+        if N == 1 and not args.no_cpu_baseline:
             line["ref_cuda_sm100"] = ref_cuda_sample(name, mode)
             try:
                 cb = cpu_reference_sample(name, mode, args.cpu_seconds)
@@ -576,15 +613,16 @@ def run_ours(args):
                                         "sample": cb["sample"], "cpu_model": cpu_model()}
             except Exception as e:  # the checker being absent must not hide the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
-    else:
-        # hoist + trace + shade per rank, + encode on rank 0
-        # hoist + trace + shade per rank; count + emit per rank (host) or on rank 0 only (ipc / nccl)
-        line["gpu_launches"] = int(((5 * world) if args.gather == "host" else (3 * world + 2)) * args.steps)
     print(json.dumps(line))
-    if renderer is not None:
-        renderer.close()
+    sys.stdout.flush()
+    if m is not None:
+        m.close()
+    ctx.close()
+    ok = line.get("parity_check", {}).get("n_gpu_equals_1_gpu", True)
     if dist is not None:
         dist.destroy_process_group()
+    if not ok:
+        raise SystemExit("N-GPU stream differs from the single-GPU stream: %r" % (line["parity_check"],))
 
 
 def main():

@@ -82,7 +82,11 @@ enum {
      * tile, groups whose bounding cone misses the tile's ray cone are skipped.  Results are identical bit for bit;
      * only the number of ray-sphere tests executed changes (rtc_timings.sphere_tests), which is why the FP32 roofline
      * is quoted with this flag off.                                                                               */
-    RTC_FLAG_CULL = 1u << 2
+    RTC_FLAG_CULL = 1u << 2,
+    /* Parity hook: also keep the hit records (distance, object index) of every ray for rtc_frame_hits.  Without it
+     * the ray kernel shades in its tile epilogue and the records never leave the SM (with RTC_FLAG_SHADOWS they are
+     * kept anyway: the shadow pass reads them).                                                                    */
+    RTC_FLAG_KEEP_HITS = 1u << 3
 };
 
 /* == RayTracingCPUToGPUData (reference RayTracingManager.h:9-19) without the vptrs.
@@ -112,6 +116,19 @@ typedef struct rtc_object {
     int32_t reserved_;
 } rtc_object;
 
+/* The light and material constants of the reference's shading call site (RayTracing.cu:143-152, :69, :77), which the
+ * reference hard-codes; rtc_set_light makes them per-context state.  The defaults are the reference's values.  The
+ * shininess stays 32 (RayTracing.cu:151).                                                                           */
+typedef struct rtc_light {
+    float pos[3];          /* (1, 50, 0)       lightPos       RayTracing.cu:146; also the origin of the shadow rays */
+    float diffuse_color;   /* 1                diffuseColor   :147                                                  */
+    float diffuse_power;   /* 2000             diffusePower   :147                                                  */
+    float specular_color;  /* 1                specColor      :148                                                  */
+    float specular_power;  /* 3000             specPower      :148                                                  */
+    float ambient[3];      /* (0.2, 0.2, 0.2)  ambient term   :77                                                   */
+    float object_specular; /* 1                the object's specular colour :78                                     */
+} rtc_light;
+
 /* Per-stage device timings of the last rtc_render on this context (CUDA events). */
 typedef struct rtc_timings {
     float prep_ms;    /* per-frame scene hoist (oc, c per sphere)          */
@@ -137,6 +154,13 @@ RTC_API const char* rtc_version(void);
  * legacy default stream: hand over an explicit stream.)                                   */
 RTC_API int rtc_set_stream(rtc_ctx* ctx, void* cuda_stream);
 RTC_API int rtc_device_info(rtc_ctx* ctx, int* sm_count, int* clock_khz, size_t* smem_optin);
+/* Wait for everything enqueued on the context's stream (the cudaDeviceSynchronize of the reference's Update,
+ * RayTracingManager.cu:126, restricted to this context).                                                              */
+RTC_API int rtc_synchronize(rtc_ctx* ctx);
+
+/* Light / material block used by the shading stage and the shadow pass of every later frame; NULL restores the
+ * reference's constants (RayTracing.cu:143-152).                                                                    */
+RTC_API int rtc_set_light(rtc_ctx* ctx, const rtc_light* light);
 
 /* ---- sink geometry: PrintMachine::Start / ChangeSize (PrintMachine.cpp:108-152,:216) - */
 RTC_API int rtc_resize(rtc_ctx* ctx, uint32_t x, uint32_t y);
@@ -172,7 +196,8 @@ RTC_API int rtc_frame_ansi_device(rtc_ctx* ctx, const char** dev_ptr, size_t* n_
 /* Parity hooks: quantised colour plane ((x-1)*y*bpp bytes, bpp = 3 for the RGB modes, 1 =
  * xterm-256 index for the 8-bit modes), glyph plane ((x-1)*y bytes, ' ' on a miss; NULL in
  * the PIXEL/NORMALS modes) and hit records (distance; object index or -1) of the last
- * rtc_render, copied to host buffers owned by the context.                               */
+ * rtc_render, copied to host buffers owned by the context.  rtc_frame_hits needs a frame
+ * rendered with RTC_FLAG_KEEP_HITS (or RTC_FLAG_SHADOWS).                                 */
 RTC_API int rtc_frame_color(rtc_ctx* ctx, const uint8_t** host_color, uint32_t* bpp,
                             const uint8_t** host_glyph);
 RTC_API int rtc_frame_hits(rtc_ctx* ctx, const float** host_dist, const int32_t** host_index);
@@ -204,6 +229,14 @@ RTC_API int rtc_last_timings(rtc_ctx* ctx, rtc_timings* out);
 RTC_API int rtc_trace_band(rtc_ctx* ctx, const rtc_params* params, rtc_mode mode,
                            uint32_t flags, uint32_t row0, uint32_t row1,
                            uint8_t* dev_color, uint8_t* dev_glyph);
+/* RayTracing::RayTrace as the reference's INNER seam delivers it (RayTracing.h:31-38, RayTracing.cu:797-867): the RAW
+ * cell buffer, rtc_raw_size(x, y) = 20*x*y bytes in DEVICE memory (4-byte aligned), one 20-byte (8-bit modes: 12-byte)
+ * cell per console position at (row*x + col)*SIZE, the newline column and everything past SIZE*x*y zero -- exactly what
+ * the reference's kernels leave in m_deviceResultArray after its per-frame memset (RayTracingManager.cu:161-165).  For
+ * callers that keep the reference's own host-side MinimizeRGB; the product path (rtc_render / rtc_update) never builds
+ * this buffer.  Asynchronous on the context's stream.                                                               */
+RTC_API int rtc_trace_raw(rtc_ctx* ctx, const rtc_params* params, rtc_mode mode, uint32_t flags, char* dev_result);
+RTC_API size_t rtc_raw_size(uint32_t x, uint32_t y);
 /* MinimizeRGB / Minimize8bit (RayTracingManager.cu:251-319 / :181-249) on the device:
  * colour plane (+glyph plane) of an x-by-y frame -> minimised stream in dev_out (capacity
  * cap bytes; rtc_encode_capacity gives the worst case).  *dev_total (8-byte device or
@@ -224,11 +257,50 @@ RTC_API size_t rtc_encode_capacity(uint32_t x, uint32_t y, rtc_mode mode);
 RTC_API uint32_t rtc_mode_bpp(rtc_mode mode);
 RTC_API uint32_t rtc_mode_has_glyph(rtc_mode mode);
 
-/* CUDA IPC plumbing so that rank g can write its band straight into rank 0's frame buffer
- * over NVLink (the gather fused into the shade kernel's stores).                          */
-RTC_API int rtc_ipc_export(rtc_ctx* ctx, void* dev_ptr, unsigned char handle_out[64]);
-RTC_API int rtc_ipc_open(rtc_ctx* ctx, const unsigned char handle[64], void** dev_ptr);
-RTC_API int rtc_ipc_close(rtc_ctx* ctx, void* dev_ptr);
+/* ---- multi-GPU frame driver: RayTracingManager::Update across the GPUs of one box ------------------------------------
+ * The reference's frame driver (RayTracingManager.h:31-35, RayTracingManager.cu:76-154) can only use one GPU.  rtc_mgpu
+ * splits the frame into contiguous row bands, one per device, in ONE process: a context, a stream and a worker thread per
+ * device, frames pipelined three deep.  The result is byte-identical to a single-GPU frame (MinimizeRGB's colour
+ * carry-over across band seams included, RayTracingManager.cu:262-301).
+ *   RTC_GATHER_HOST  every device encodes its own band and copies its piece of the stream over its own PCIe link into
+ *                    one pinned host frame, at the offset given by the lengths of the devices before it;
+ *   RTC_GATHER_P2P   every device's ray kernel stores its quantised band straight into device 0's frame planes over
+ *                    NVLink (peer stores), device 0 encodes the whole frame and copies the stream out.
+ * device_ids == NULL means 0..n_gpus-1; an id may appear more than once (several bands on one GPU: tests).            */
+typedef struct rtc_mgpu rtc_mgpu;
+enum { RTC_GATHER_HOST = 0, RTC_GATHER_P2P = 1 };
+RTC_API int rtc_mgpu_create(rtc_mgpu** out, int n_gpus, const int* device_ids, int gather);
+RTC_API void rtc_mgpu_destroy(rtc_mgpu* m);
+RTC_API int rtc_mgpu_count(rtc_mgpu* m);
+/* Borrowed per-device context (device info, timings); do not destroy it.                                             */
+RTC_API int rtc_mgpu_context(rtc_mgpu* m, int i, rtc_ctx** out);
+/* Scene3D (Scene3D.cpp:36-105), replicated on every device.  The mutators may be called with frames in flight: they
+ * are queued and take effect, in order, with the next submitted frame.  get_objects needs an idle pipeline.           */
+RTC_API int rtc_mgpu_scene_clear(rtc_mgpu* m);
+RTC_API int rtc_mgpu_scene_add_sphere(rtc_mgpu* m, const float center[3], float radius, const float rgb[3], float speed, int mover);
+RTC_API int rtc_mgpu_scene_add_plane(rtc_mgpu* m, const float center[3], const float normal[3], const float rgb[3],
+                                     float width, float height);
+RTC_API int rtc_mgpu_scene_set_objects(rtc_mgpu* m, const rtc_object* objs, uint32_t n);
+RTC_API int rtc_mgpu_scene_get_objects(rtc_mgpu* m, rtc_object* out, uint32_t cap, uint32_t* n);
+RTC_API int rtc_mgpu_set_light(rtc_mgpu* m, const rtc_light* light);
+/* RayTracingManager::Update, pipelined like rtc_submit / rtc_collect (at most three frames in flight): submit enqueues
+ * physics step + band trace + shade (+ band encode) on every device and returns at once; collect returns the OLDEST
+ * submitted frame's stream in pinned host memory, valid until the third rtc_mgpu_submit after the one that made it.   */
+RTC_API int rtc_mgpu_submit(rtc_mgpu* m, const rtc_params* params, rtc_mode mode, double dt, uint32_t flags);
+RTC_API int rtc_mgpu_collect(rtc_mgpu* m, const char** host_ptr, size_t* n_bytes);
+/* submit + collect as one synchronous call (== RayTracingManager::Update).                                            */
+RTC_API int rtc_mgpu_update(rtc_mgpu* m, const rtc_params* params, rtc_mode mode, double dt, uint32_t flags,
+                            const char** host_ptr, size_t* n_bytes);
+/* Of the last collected frame: per-device time of its kernels (CUDA events on each device's stream), the band
+ * boundaries rows[0..n_gpus], and (P2P) device 0's encode time.  Any pointer may be NULL.                             */
+RTC_API int rtc_mgpu_last_frame(rtc_mgpu* m, float* device_ms, uint32_t* rows, float* encode_ms);
+/* Explicit band boundaries rows[0..n_gpus] for frames of height y (NULL: automatic -- equal bands; in the P2P gather
+ * device 0's band shrinks by the measured cost of the encoder).                                                       */
+RTC_API int rtc_mgpu_set_bands(rtc_mgpu* m, uint32_t y, const uint32_t* rows);
+/* Measurement helper: the next submit first overwrites 256 MiB on every device (evicts the 126 MB L2), untimed.       */
+RTC_API int rtc_mgpu_flush_l2(rtc_mgpu* m);
+/* The band planner itself (host only, no GPU): see rtc_mgpu.cu.                                                       */
+RTC_API int rtc_plan_bands(uint32_t y, int n, uint32_t align, double deficit_rows, uint32_t wave_units, uint32_t* rows_out);
 
 /* ---- host-side helpers that need no GPU (reference host code on the path) -------------- */
 /* Camera3D::Init + Update + GetInverseVMatrix + Engine3D::Render's parameter block

@@ -63,6 +63,7 @@ MODE_NAMES = ["BIT_ASCII", "BIT_PIXEL", "RGB_ASCII", "RGB_PIXEL", "RGB_NORMALS",
 FLAG_SHADOWS = 1
 FLAG_UPDATE_REF_LAUNCH_LIMIT = 2
 FLAG_CULL = 4
+FLAG_KEEP_HITS = 8
 
 
 def mode_bpp(mode):

@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["rtc_api.cu", "rtc_trace.cu", "rtc_shade.cu", "rtc_encode.cu", "rtc_microbench.cu", "rtc_camera.cpp"]
+SOURCES = ["rtc_api.cu", "rtc_mgpu.cu", "rtc_trace.cu", "rtc_shade.cu", "rtc_encode.cu", "rtc_microbench.cu", "rtc_camera.cpp"]
 LIB = os.path.join(HERE, "librtc_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

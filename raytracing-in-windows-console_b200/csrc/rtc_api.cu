@@ -21,12 +21,11 @@
 #include <utility>
 #include <vector>
 
-#include "rtc_device.cuh"
-#include "rtc_kernels.h"
+#include "rtc_ctx.h"
 
-namespace {
+namespace rtc {
 
-thread_local char g_err[512] = "";
+static thread_local char g_err[512] = "";
 
 int fail(int code, const char* fmt, ...)
 {
@@ -37,110 +36,15 @@ int fail(int code, const char* fmt, ...)
     return code;
 }
 
-#define CK(call)                                                                                         \
-    do {                                                                                                 \
-        cudaError_t e_ = (call);                                                                         \
-        if (e_ != cudaSuccess)                                                                           \
-            return fail(RTC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-    } while (0)
+}  // namespace rtc
 
-inline bool mode_is_8bit(int m) { return m == RTC_BIT_ASCII || m == RTC_BIT_PIXEL; }
-inline bool mode_has_glyph(int m) { return m == RTC_BIT_ASCII || m == RTC_RGB_ASCII; }
-inline uint32_t mode_bpp(int m) { return mode_is_8bit(m) ? 1u : 3u; }
-inline uint32_t mode_cell(int m) { return mode_is_8bit(m) ? 12u : 20u; }
-
-template <class T>
-struct DevBuf {
-    T* p = nullptr;
-    size_t cap = 0;   // elements
-    cudaError_t ensure(size_t n)
-    {
-        if (n <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
-        if (e == cudaSuccess) cap = n;
-        return e;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
-template <class T>
-struct PinBuf {
-    T* p = nullptr;
-    size_t cap = 0;
-    cudaError_t ensure(size_t n)
-    {
-        if (n <= cap) return cudaSuccess;
-        if (p) cudaFreeHost(p);
-        p = nullptr; cap = 0;
-        cudaError_t e = cudaMallocHost(&p, n * sizeof(T));
-        if (e == cudaSuccess) cap = n;
-        return e;
-    }
-    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
-};
-
-}  // namespace
-
-struct rtc_ctx {
-    int device = 0;
-    int sm_count = 0;
-    int clock_khz = 0;
-    size_t smem_optin = 0;
-    cudaStream_t own_stream = nullptr;
-    cudaStream_t stream = nullptr;
-    uint32_t x = 0, y = 0;
-
-    // scene (host master copy + device mirror)
-    std::vector<rtc_object> objs;
-    std::vector<int32_t> sphere_obj, plane_obj;
-    bool scene_dirty = true;       // host -> device upload pending
-    bool host_stale = false;       // device physics ran; host copy must be refreshed before use
-    // device scene: ONE blob [objects | sphere index list | plane index list] so that an upload is a single copy
-    DevBuf<unsigned char> d_scene;
-    struct View { rtc_object* p = nullptr; } d_objs;
-    struct ViewI { int32_t* p = nullptr; } d_sphere_obj, d_plane_obj;
-    DevBuf<float> d_fast;      // 12 B per sphere slot (slots padded to a multiple of 4)
-    DevBuf<float4> d_exact;
-    DevBuf<float> d_dmin, d_dmin_l;   // per group of 4 spheres: lower bound of any hit distance (camera / light origin)
-    DevBuf<float4> d_cone, d_cone_l;  // per group: bounding cone seen from the origin (axis, cos half-angle) ...
-    DevBuf<float> d_sin, d_sin_l;     // ... and the sine of its half-angle (RTC_FLAG_CULL)
-    DevBuf<float> d_fast_l;    // the same hoist with the light as origin (shadow-ray extension)
-    DevBuf<float4> d_exact_l;
-    DevBuf<uint8_t> d_shadow;  // 1 byte per pixel: occluded
-
-    // frame buffers
-    DevBuf<float> d_hit_t;
-    DevBuf<int32_t> d_hit_idx;
-    DevBuf<uint8_t> d_color, d_glyph;
-    DevBuf<char> d_out[2];                  // two frame slots: the stream of frame k is copied out while k+1 is encoded
-    DevBuf<unsigned char> d_desc;           // encoder scratch: per-tile counts, group accumulators (two parities)
-    uint32_t enc_parity = 0;
-    DevBuf<unsigned int> d_counters;        // zeroed by the hoist every frame: [0..27] tile tickets of the primary pass (one per
-                                            // sphere chunk), [32..59] of the shadow pass, [60..63] two 64-bit counts of groups tested
-    DevBuf<unsigned long long> d_total;     // [2]
-    DevBuf<float> d_sink;
-    PinBuf<unsigned long long> h_total;     // [2]
-    PinBuf<char> h_out[2];
-    PinBuf<unsigned char> h_scene[2];       // pinned staging of the scene upload (objects + index lists)
-    int scene_slot = 0;
-    cudaStream_t copy_stream = nullptr;     // D2H of finished streams, concurrent with the next frame's kernels
-    cudaEvent_t ev_total[2] = {nullptr, nullptr};   // slot's encode finished and its length is on the host
-    int cur = 0;                            // slot of the last rtc_render
-    int fifo[2] = {0, 0}, fifo_n = 0;       // submitted, not yet collected slots (oldest first)
-    size_t slot_cap[2] = {0, 0};
-    PinBuf<uint8_t> h_color, h_glyph;
-    PinBuf<float> h_hit_t;
-    PinBuf<int32_t> h_hit_idx;
-
-    // last frame
-    bool have_frame = false;
-    int last_mode = RTC_RGB_PIXEL;
-    uint32_t last_x = 0, last_y = 0;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    bool timings_valid = false;
-    uint32_t last_launches = 0;
-};
+using rtc::DevBuf;
+using rtc::PinBuf;
+using rtc::fail;
+using rtc::mode_bpp;
+using rtc::mode_cell;
+using rtc::mode_has_glyph;
+using rtc::mode_is_8bit;
 
 namespace {
 
@@ -209,15 +113,18 @@ int upload_scene(rtc_ctx* c)
     c->d_plane_obj.p = reinterpret_cast<int32_t*>(c->d_scene.p + b_objs + b_sph);
     c->scene_slot ^= 1;
     PinBuf<unsigned char>& st = c->h_scene[c->scene_slot];
-    if (b_all > st.cap) {
-        CK(cudaStreamSynchronize(c->stream));
-        CK(st.ensure(b_all * 2));
+    if (c->scene_pending[c->scene_slot]) {                      // an earlier upload may still be reading this slot
+        CK(cudaEventSynchronize(c->ev_scene[c->scene_slot]));
+        c->scene_pending[c->scene_slot] = false;
     }
+    if (b_all > st.cap) CK(st.ensure(b_all * 2));
     unsigned char* h = st.p;
     if (n) memcpy(h, c->objs.data(), n * sizeof(rtc_object));
     if (!c->sphere_obj.empty()) memcpy(h + b_objs, c->sphere_obj.data(), c->sphere_obj.size() * sizeof(int32_t));
     if (!c->plane_obj.empty()) memcpy(h + b_objs + b_sph, c->plane_obj.data(), c->plane_obj.size() * sizeof(int32_t));
     CK(cudaMemcpyAsync(c->d_scene.p, h, b_all - 64, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaEventRecord(c->ev_scene[c->scene_slot], c->stream));
+    c->scene_pending[c->scene_slot] = true;
     c->scene_dirty = false;
     return RTC_OK;
 }
@@ -244,15 +151,33 @@ rtc::FrameParams make_frame(const rtc_params* p, uint32_t row0, uint32_t row1)
     return f;
 }
 
-// Encoder scratch: zeroed when (re)allocated; afterwards every launch zeroes the accumulators of the next one.
-int encode_scratch(rtc_ctx* c, uint64_t n_cells)
+}  // namespace
+
+namespace rtc {
+
+// The encoder as one step: scratch, parity, launches.  The scratch is zeroed when (re)allocated; afterwards every count
+// launch zeroes the accumulators of the NEXT one, so the parity may flip only when a count kernel is really enqueued
+// (SDL frames, 1-column consoles and failed renders launch none and must leave it alone).
+int do_encode(rtc_ctx* c, const uint8_t* d_color, const uint8_t* d_glyph, uint32_t x, uint32_t rows, int mode, char* d_out,
+              size_t cap, unsigned long long* d_total, bool continues)
 {
-    const size_t need = rtc::encode_state_bytes(n_cells);
-    if (need > c->d_desc.cap) {
-        CK(c->d_desc.ensure(need + need / 2));                  // head-room: growing frames do not reallocate every time
-        CK(cudaMemsetAsync(c->d_desc.p, 0, c->d_desc.cap, c->stream));
+    const bool counts = mode != RTC_SDL && x > 1u && rows > 0u;
+    if (counts) {
+        const size_t need = rtc::encode_state_bytes((uint64_t)(x - 1u) * rows);
+        if (need > c->d_desc.cap) {
+            CK(c->d_desc.ensure(need + need / 2));              // head-room: growing frames do not reallocate every time
+            CK(cudaMemsetAsync(c->d_desc.p, 0, c->d_desc.cap, c->stream));
+        }
     }
-    c->enc_parity ^= 1u;
+    const uint32_t parity = c->enc_parity ^ (counts ? 1u : 0u);
+    const cudaError_t e = rtc::launch_encode(c->stream, d_color, d_glyph, x, rows, mode, d_out, cap, d_total, c->d_desc.p,
+                                             c->d_desc.cap, parity, continues);
+    if (e != cudaSuccess) {
+        // a launch may or may not have run: put the accumulators of both parities back into the known state
+        if (c->d_desc.p) cudaMemsetAsync(c->d_desc.p, 0, c->d_desc.cap, c->stream);
+        return fail(RTC_ERR_CUDA, "ANSI encoder launch failed: %s", cudaGetErrorString(e));
+    }
+    c->enc_parity = parity;
     return RTC_OK;
 }
 
@@ -280,24 +205,32 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
 
     c->last_launches++;
     const bool shadows = (flags & RTC_FLAG_SHADOWS) != 0 && mode != RTC_SDL && mode != RTC_RGB_NORMALS;
+    // Without shadow rays the ray kernel shades + quantises in its tile epilogue (one launch, no hit-record round trip);
+    // hit records are then written only on request.  With shadow rays the records feed the light-origin pass and the
+    // stand-alone shade kernel runs after it.
+    const bool fused = !shadows && mode != RTC_SDL;
+    const bool keep_hits = (flags & RTC_FLAG_KEEP_HITS) != 0 || shadows;
     if (shadows) {
         CK(c->d_fast_l.ensure(n_slots > 0 ? 3 * (size_t)n_slots : 12));
         CK(c->d_exact_l.ensure(n_slots > 0 ? n_slots : 4));
         CK(c->d_dmin_l.ensure(n_slots > 0 ? n_slots / 4 + 4 : 4));
         CK(c->d_cone_l.ensure(n_slots > 0 ? n_slots / 4 + 4 : 4));
         CK(c->d_sin_l.ensure(n_slots > 0 ? n_slots / 4 + 4 : 4));
-        CK(rtc::launch_hoist(c->stream, c->d_objs.p, c->d_sphere_obj.p, n_spheres, n_slots, rtc::kLightPos, c->d_fast_l.p,
+        CK(rtc::launch_hoist(c->stream, c->d_objs.p, c->d_sphere_obj.p, n_spheres, n_slots, c->shade.light, c->d_fast_l.p,
                              c->d_exact_l.p, c->d_dmin_l.p, c->d_cone_l.p, c->d_sin_l.p, c->d_counters.p, 0));
         c->last_launches++;
     }
     if (record_events) CK(cudaEventRecord(c->ev[1], c->stream));
+    c->hits_valid = false;
     if (n_px > 0) {
-        CK(c->d_hit_t.ensure(n_px));
-        CK(c->d_hit_idx.ensure(n_px));
         const rtc::FrameParams fp = make_frame(p, row0, row1);
         const rtc::TracePlan plan = rtc::plan_trace(p->x, row1 - row0, n_slots, c->sm_count);
         const int n_chunks = n_slots == 0 ? 1 : (n_slots + plan.max_slots - 1) / plan.max_slots;
         if (n_chunks > rtc::kMaxChunks) return fail(RTC_ERR_CAPACITY, "too many spheres (%d)", n_spheres);
+        if (keep_hits || n_chunks > 1) {
+            CK(c->d_hit_t.ensure(n_px));
+            CK(c->d_hit_idx.ensure(n_px));
+        }
         for (int ch = 0; ch < n_chunks; ++ch) {
             const int s0 = ch * plan.max_slots;
             const int slots = n_slots - s0 < plan.max_slots ? n_slots - s0 : plan.max_slots;
@@ -306,9 +239,11 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
             CK(rtc::launch_trace(c->stream, c->sm_count, fp, c->d_fast.p + 3 * (size_t)s0, c->d_exact.p + s0, c->d_dmin.p + s0 / 4,
                                  c->d_cone.p + s0 / 4, c->d_sin.p + s0 / 4, c->d_sphere_obj.p + s0,
                                  sph, slots, c->d_objs.p, c->d_plane_obj.p, last ? n_planes : 0, c->d_hit_t.p,
-                                 c->d_hit_idx.p, c->d_counters.p + ch, ch > 0 ? 1 : 0, nullptr, nullptr, plan.threads, cull, stats));
+                                 c->d_hit_idx.p, c->d_counters.p + ch, ch > 0 ? 1 : 0, nullptr, nullptr, plan.threads, cull, stats,
+                                 c->shade, fused && last ? mode : -1, d_color, d_glyph, !last || keep_hits));
             c->last_launches++;
         }
+        c->hits_valid = keep_hits;
         if (shadows) {                                          // second pass: one ray per shaded pixel, cast from the light
             CK(c->d_shadow.ensure(n_px));
             for (int ch = 0; ch < n_chunks; ++ch) {
@@ -319,15 +254,15 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
                 CK(rtc::launch_trace(c->stream, c->sm_count, fp, c->d_fast_l.p + 3 * (size_t)s0, c->d_exact_l.p + s0,
                                      c->d_dmin_l.p + s0 / 4, c->d_cone_l.p + s0 / 4, c->d_sin_l.p + s0 / 4, c->d_sphere_obj.p + s0, sph, slots,
                                      c->d_objs.p, c->d_plane_obj.p, last ? n_planes : 0,
-                                     c->d_hit_t.p, c->d_hit_idx.p, c->d_counters.p + 32 + ch, ch > 0 ? 1 : 0, rtc::kLightPos,
-                                     c->d_shadow.p, plan.threads, cull, stats + 1));
+                                     c->d_hit_t.p, c->d_hit_idx.p, c->d_counters.p + 32 + ch, ch > 0 ? 1 : 0, c->shade.light,
+                                     c->d_shadow.p, plan.threads, cull, stats + 1, c->shade, -1, nullptr, nullptr, false));
                 c->last_launches++;
             }
         }
         if (record_events) CK(cudaEventRecord(c->ev[2], c->stream));
-        if (mode != RTC_SDL) {
-            CK(rtc::launch_shade(c->stream, fp, mode, flags, c->d_objs.p, (int)c->objs.size(), c->d_hit_t.p,
-                                 c->d_hit_idx.p, shadows ? c->d_shadow.p : nullptr, d_color, d_glyph));
+        if (shadows) {
+            CK(rtc::launch_shade(c->stream, fp, c->shade, mode, c->d_objs.p, c->d_hit_t.p, c->d_hit_idx.p, c->d_shadow.p,
+                                 d_color, d_glyph));
             c->last_launches++;
         }
         if (record_events) CK(cudaEventRecord(c->ev[3], c->stream));
@@ -338,11 +273,14 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
     return RTC_OK;
 }
 
-}  // namespace
+}  // namespace rtc
+
+using rtc::do_encode;
+using rtc::trace_shade;
 
 extern "C" {
 
-const char* rtc_last_error(void) { return g_err; }
+const char* rtc_last_error(void) { return rtc::g_err; }
 const char* rtc_version(void) { return "rtc_b200 0.1 (sm_100a)"; }
 
 uint32_t rtc_mode_bpp(rtc_mode mode) { return mode_bpp(mode); }
@@ -392,6 +330,7 @@ int rtc_create(rtc_ctx** out, int device)
     CKC(c->d_total.ensure(2));
     CKC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (auto& ev : c->ev_total) CKC(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto& ev : c->ev_scene) CKC(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CKC(c->d_sink.ensure(4));
     CKC(c->h_total.ensure(2));
 #undef CKC
@@ -412,6 +351,7 @@ void rtc_destroy(rtc_ctx* c)
     c->h_total.release(); c->h_out[0].release(); c->h_out[1].release(); c->h_scene[0].release(); c->h_scene[1].release();
     c->h_color.release(); c->h_glyph.release();
     for (auto& ev : c->ev_total) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c->ev_scene) if (ev) cudaEventDestroy(ev);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     c->h_hit_t.release(); c->h_hit_idx.release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
@@ -432,6 +372,23 @@ int rtc_device_info(rtc_ctx* c, int* sm_count, int* clock_khz, size_t* smem_opti
     if (sm_count) *sm_count = c->sm_count;
     if (clock_khz) *clock_khz = c->clock_khz;
     if (smem_optin) *smem_optin = c->smem_optin;
+    return RTC_OK;
+}
+
+int rtc_synchronize(rtc_ctx* c)
+{
+    if (!c) return fail(RTC_ERR_INVALID, "ctx is NULL");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return RTC_OK;
+}
+
+int rtc_set_light(rtc_ctx* c, const rtc_light* l)
+{
+    if (!c) return fail(RTC_ERR_INVALID, "ctx is NULL");
+    static_assert(sizeof(rtc_light) == sizeof(rtc::ShadeParams), "rtc_light and ShadeParams are the same 11 floats");
+    const rtc_light def = {{1.0f, 50.0f, 0.0f}, 1.0f, 2000.0f, 1.0f, 3000.0f, {0.2f, 0.2f, 0.2f}, 1.0f};
+    memcpy(&c->shade, l ? l : &def, sizeof c->shade);
     return RTC_OK;
 }
 
@@ -456,6 +413,7 @@ int rtc_scene_clear(rtc_ctx* c)
 int rtc_scene_add_sphere(rtc_ctx* c, const float center[3], float radius, const float rgb[3], float speed, int mover)
 {
     if (!c || !center || !rgb) return fail(RTC_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(c->device));
     int rc = refresh_host_scene(c);
     if (rc) return rc;
     rtc_object o;
@@ -471,6 +429,7 @@ int rtc_scene_add_sphere(rtc_ctx* c, const float center[3], float radius, const 
 int rtc_scene_add_plane(rtc_ctx* c, const float center[3], const float normal[3], const float rgb[3], float width, float height)
 {
     if (!c || !center || !normal || !rgb) return fail(RTC_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(c->device));
     int rc = refresh_host_scene(c);
     if (rc) return rc;
     rtc_object o;
@@ -501,6 +460,7 @@ int rtc_scene_set_objects(rtc_ctx* c, const rtc_object* objs, uint32_t n)
 int rtc_scene_get_objects(rtc_ctx* c, rtc_object* out, uint32_t cap, uint32_t* n)
 {
     if (!c) return fail(RTC_ERR_INVALID, "ctx is NULL");
+    CK(cudaSetDevice(c->device));
     int rc = refresh_host_scene(c);
     if (rc) return rc;
     if (n) *n = (uint32_t)c->objs.size();
@@ -538,6 +498,7 @@ int rtc_render(rtc_ctx* c, const rtc_params* p, rtc_mode mode, uint32_t flags)
     CK(cudaSetDevice(c->device));
     if (p->x < 1 || p->y < 1) return fail(RTC_ERR_INVALID, "invalid console size %ux%u", p->x, p->y);
     if ((uint64_t)(p->x - 1u) * p->y >= (1ull << 31)) return fail(RTC_ERR_CAPACITY, "console size too large");
+    if (mode < RTC_BIT_ASCII || mode > RTC_SDL) return fail(RTC_ERR_INVALID, "invalid rendering mode %d", (int)mode);
     const uint32_t W = p->x - 1u;
     const size_t n_px = (size_t)W * p->y;
     const size_t cap = rtc_encode_capacity(p->x, p->y, mode);
@@ -545,13 +506,12 @@ int rtc_render(rtc_ctx* c, const rtc_params* p, rtc_mode mode, uint32_t flags)
     if (mode_has_glyph(mode)) CK(c->d_glyph.ensure(n_px + 16));
     const int slot = c->cur ^ 1;                               // the other slot may still be draining to the host
     CK(c->d_out[slot].ensure(cap));
-    int rc0 = encode_scratch(c, n_px);
-    if (rc0) return rc0;
     c->have_frame = false;
     int rc = trace_shade(c, p, mode, flags, 0, p->y, c->d_color.p, mode_has_glyph(mode) ? c->d_glyph.p : nullptr, true);
     if (rc) return rc;
-    CK(rtc::launch_encode(c->stream, c->d_color.p, mode_has_glyph(mode) ? c->d_glyph.p : nullptr, p->x, p->y, mode,
-                          c->d_out[slot].p, cap, c->d_total.p + slot, c->d_desc.p, c->d_desc.cap, c->enc_parity));
+    rc = do_encode(c, c->d_color.p, mode_has_glyph(mode) ? c->d_glyph.p : nullptr, p->x, p->y, mode, c->d_out[slot].p, cap,
+                   c->d_total.p + slot, false);
+    if (rc) return rc;
     c->last_launches += 2;
     CK(cudaEventRecord(c->ev[4], c->stream));
     CK(cudaMemcpyAsync(c->h_total.p + slot, c->d_total.p + slot, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
@@ -648,6 +608,7 @@ int rtc_frame_hits(rtc_ctx* c, const float** host_dist, const int32_t** host_ind
 {
     if (!c) return fail(RTC_ERR_INVALID, "ctx is NULL");
     if (!c->have_frame) return fail(RTC_ERR_INVALID, "no frame rendered");
+    if (!c->hits_valid) return fail(RTC_ERR_INVALID, "the last frame kept no hit records: render it with RTC_FLAG_KEEP_HITS");
     CK(cudaSetDevice(c->device));
     const size_t n_px = (size_t)(c->last_x - 1u) * c->last_y;
     CK(c->h_hit_t.ensure(n_px + 1));
@@ -705,6 +666,25 @@ int rtc_trace_band(rtc_ctx* c, const rtc_params* p, rtc_mode mode, uint32_t flag
     return trace_shade(c, p, mode, flags, row0, row1, dev_color, dev_glyph, false);
 }
 
+int rtc_trace_raw(rtc_ctx* c, const rtc_params* p, rtc_mode mode, uint32_t flags, char* dev_result)
+{
+    if (!c || !p || !dev_result) return fail(RTC_ERR_INVALID, "NULL argument");
+    if (mode < RTC_BIT_ASCII || mode > RTC_SDL) return fail(RTC_ERR_INVALID, "invalid rendering mode %d", (int)mode);   // (the reference asserts)
+    if (p->x < 1 || p->y < 1) return fail(RTC_ERR_INVALID, "invalid console size %ux%u", p->x, p->y);
+    if ((uint64_t)(p->x - 1u) * p->y >= (1ull << 31)) return fail(RTC_ERR_CAPACITY, "console size too large");
+    CK(cudaSetDevice(c->device));
+    const size_t n_px = (size_t)(p->x - 1u) * p->y;
+    CK(c->d_color.ensure(n_px * mode_bpp(mode) + 16));
+    if (mode_has_glyph(mode)) CK(c->d_glyph.ensure(n_px + 16));
+    c->have_frame = false;
+    int rc = trace_shade(c, p, mode, flags, 0, p->y, c->d_color.p, mode_has_glyph(mode) ? c->d_glyph.p : nullptr, false);
+    if (rc) return rc;
+    CK(rtc::launch_expand_raw(c->stream, c->d_color.p, mode_has_glyph(mode) ? c->d_glyph.p : nullptr, p->x, p->y, mode, dev_result));
+    return RTC_OK;
+}
+
+size_t rtc_raw_size(uint32_t x, uint32_t y) { return (size_t)20 * x * y; }
+
 int rtc_encode(rtc_ctx* c, const uint8_t* dev_color, const uint8_t* dev_glyph, uint32_t x, uint32_t y, rtc_mode mode,
                char* dev_out, size_t cap, unsigned long long* dev_total)
 {
@@ -715,11 +695,7 @@ int rtc_encode(rtc_ctx* c, const uint8_t* dev_color, const uint8_t* dev_glyph, u
     if (mode != RTC_SDL && x > 1 && !dev_color) return fail(RTC_ERR_INVALID, "dev_color is NULL");
     if ((uint64_t)(x - 1u) * y >= (1ull << 31)) return fail(RTC_ERR_CAPACITY, "console size too large");
     CK(cudaSetDevice(c->device));
-    int rc = encode_scratch(c, (uint64_t)(x - 1u) * y);
-    if (rc) return rc;
-    CK(rtc::launch_encode(c->stream, dev_color, dev_glyph, x, y, mode, dev_out, cap, dev_total, c->d_desc.p, c->d_desc.cap,
-                          c->enc_parity));
-    return RTC_OK;
+    return do_encode(c, dev_color, dev_glyph, x, y, mode, dev_out, cap, dev_total, false);
 }
 
 int rtc_encode_band(rtc_ctx* c, const uint8_t* dev_color, const uint8_t* dev_glyph, uint32_t x, uint32_t rows, rtc_mode mode,
@@ -736,11 +712,7 @@ int rtc_encode_band(rtc_ctx* c, const uint8_t* dev_color, const uint8_t* dev_gly
         CK(cudaMemsetAsync(dev_total, 0, sizeof(unsigned long long), c->stream));
         return RTC_OK;
     }
-    int rc = encode_scratch(c, (uint64_t)(x - 1u) * rows);
-    if (rc) return rc;
-    CK(rtc::launch_encode(c->stream, dev_color, dev_glyph, x, rows, mode, dev_out, cap, dev_total, c->d_desc.p, c->d_desc.cap,
-                          c->enc_parity, continues != 0));
-    return RTC_OK;
+    return do_encode(c, dev_color, dev_glyph, x, rows, mode, dev_out, cap, dev_total, continues != 0);
 }
 
 int rtc_debug_ansi256_cube(rtc_ctx* c, uint8_t* dev_out)
@@ -748,35 +720,6 @@ int rtc_debug_ansi256_cube(rtc_ctx* c, uint8_t* dev_out)
     if (!c || !dev_out) return fail(RTC_ERR_INVALID, "NULL argument");
     CK(cudaSetDevice(c->device));
     CK(rtc::launch_ansi256_cube(c->stream, dev_out));
-    return RTC_OK;
-}
-
-int rtc_ipc_export(rtc_ctx* c, void* dev_ptr, unsigned char handle_out[64])
-{
-    if (!c || !dev_ptr || !handle_out) return fail(RTC_ERR_INVALID, "NULL argument");
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
-    CK(cudaSetDevice(c->device));
-    cudaIpcMemHandle_t h;
-    CK(cudaIpcGetMemHandle(&h, dev_ptr));
-    memcpy(handle_out, &h, 64);
-    return RTC_OK;
-}
-
-int rtc_ipc_open(rtc_ctx* c, const unsigned char handle[64], void** dev_ptr)
-{
-    if (!c || !handle || !dev_ptr) return fail(RTC_ERR_INVALID, "NULL argument");
-    CK(cudaSetDevice(c->device));
-    cudaIpcMemHandle_t h;
-    memcpy(&h, handle, 64);
-    CK(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
-    return RTC_OK;
-}
-
-int rtc_ipc_close(rtc_ctx* c, void* dev_ptr)
-{
-    if (!c || !dev_ptr) return fail(RTC_ERR_INVALID, "NULL argument");
-    CK(cudaSetDevice(c->device));
-    CK(cudaIpcCloseMemHandle(dev_ptr));
     return RTC_OK;
 }
 
@@ -795,13 +738,11 @@ int rtc_fp32_peak(rtc_ctx* c, int variant, int iters, float* tflops, float* ms)
     CK(rtc::launch_fp32_peak(c->stream, variant, n_ctas, iters > 8 ? 8 : iters, c->d_sink.p));   // warm-up
     CK(cudaEventRecord(c->ev[5], c->stream));
     CK(rtc::launch_fp32_peak(c->stream, variant, n_ctas, iters, c->d_sink.p));
-    cudaEvent_t end;
-    CK(cudaEventCreate(&end));
-    CK(cudaEventRecord(end, c->stream));
-    CK(cudaEventSynchronize(end));
+    CK(cudaEventRecord(c->ev[4], c->stream));                   // (ev[4] is re-recorded by the next rtc_render)
+    CK(cudaEventSynchronize(c->ev[4]));
     float t = 0.f;
-    CK(cudaEventElapsedTime(&t, c->ev[5], end));
-    cudaEventDestroy(end);
+    CK(cudaEventElapsedTime(&t, c->ev[5], c->ev[4]));
+    c->timings_valid = false;
     if (ms) *ms = t;
     *tflops = (float)(rtc::fp32_peak_flops(variant, n_ctas, iters) / (t * 1e-3) / 1e12);
     return RTC_OK;

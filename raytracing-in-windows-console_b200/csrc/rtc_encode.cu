@@ -412,6 +412,62 @@ __global__ void newline_kernel(char* __restrict__ out, uint32_t y, unsigned long
     if (i == 0) *total = y;
 }
 
+// ---- compatibility: the reference's RAW cell buffer --------------------------------------------------------------------
+// What RayTracing::RayTrace leaves in `resultArray` (RayTracing.cu:585-608 and siblings): one SIZE-byte cell per console
+// position at (row * x + col) * SIZE, SIZE = 20 (RGB modes) or 12 (8-bit modes), every traced cell written in full
+// (NUL-padded digits), the newline column x-1 left zero.  The product path never materialises this buffer (the encoder
+// goes from the planes straight to the minimised stream); it exists for callers that keep the reference's own host-side
+// MinimizeRGB / Minimize8bit, and as a parity hook (tests compare it with the reference's raw buffer byte for byte).
+template <int BPP, bool GLYPH>
+__global__ void __launch_bounds__(256)
+expand_raw_kernel(const uint8_t* __restrict__ color, const uint8_t* __restrict__ glyph, uint32_t x, uint32_t y, uint32_t* __restrict__ out)
+{
+    constexpr int NWC = BPP == 3 ? 5 : 3;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)x * y) return;
+    const uint32_t row = (uint32_t)(i / x), col = (uint32_t)(i - (size_t)row * x);
+    uint32_t c[NWC];
+#pragma unroll
+    for (int j = 0; j < NWC; ++j) c[j] = 0u;
+    if (col + 1u < x) {
+        const size_t cell = (size_t)row * (x - 1u) + col;
+        const uint32_t g = GLYPH ? (uint32_t)glyph[cell] : 32u;
+        const uint32_t fg = (GLYPH && g != 32u) ? (uint32_t)'3' : (uint32_t)'4';
+        const uint32_t mch = 'm' | (g << 8);
+        c[0] = 0x1bu | ('[' << 8) | (fg << 16) | ('8' << 24);
+        if (BPP == 3) {
+            const uint32_t lr = d_digit_lut.v[color[cell * 3]], lg = d_digit_lut.v[color[cell * 3 + 1]], lb = d_digit_lut.v[color[cell * 3 + 2]];
+            c[1] = prmt(';' | ('2' << 8) | (';' << 16), lr, 0x4210u);
+            c[2 % NWC] = prmt(lr, lg, 0x4321u);
+            c[3 % NWC] = prmt(lg, lb, 0x4321u);
+            c[NWC - 1] = prmt(lb, mch, 0x5421u);
+        } else {
+            const uint32_t li8 = d_digit_lut.v[color[cell]];
+            c[1] = prmt(';' | ('5' << 8) | (';' << 16), li8, 0x4210u);
+            c[NWC - 1] = prmt(li8, mch, 0x5421u);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NWC; ++j) out[i * NWC + j] = c[j];
+}
+
+cudaError_t launch_expand_raw(cudaStream_t st, const uint8_t* color, const uint8_t* glyph, uint32_t x, uint32_t y, int mode, char* out)
+{
+    const size_t n = (size_t)x * y;
+    if (n == 0) return cudaSuccess;
+    if (reinterpret_cast<uintptr_t>(out) & 3u) return cudaErrorInvalidValue;
+    const bool bit8 = mode == RTC_BIT_ASCII || mode == RTC_BIT_PIXEL;
+    const bool gl = (mode == RTC_BIT_ASCII || mode == RTC_RGB_ASCII) && glyph != nullptr;
+    cudaError_t e;
+    if (mode == RTC_SDL) return cudaMemsetAsync(out, 0, 20 * n, st);          // RayTrace_SDL writes nothing into the cleared buffer
+    if (bit8 && (e = cudaMemsetAsync(out + 12 * n, 0, 8 * n, st)) != cudaSuccess) return e;   // the reference clears all 20*x*y bytes
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    uint32_t* o = reinterpret_cast<uint32_t*>(out);
+    if (bit8) { if (gl) expand_raw_kernel<1, true><<<grid, 256, 0, st>>>(color, glyph, x, y, o); else expand_raw_kernel<1, false><<<grid, 256, 0, st>>>(color, glyph, x, y, o); }
+    else      { if (gl) expand_raw_kernel<3, true><<<grid, 256, 0, st>>>(color, glyph, x, y, o); else expand_raw_kernel<3, false><<<grid, 256, 0, st>>>(color, glyph, x, y, o); }
+    return cudaGetLastError();
+}
+
 static size_t enc_smem() { return 1024 + (size_t)kEncWarps * kEncStageBytes; }
 
 cudaError_t configure_encode()

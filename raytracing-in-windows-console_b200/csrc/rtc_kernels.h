@@ -8,6 +8,7 @@
 namespace rtc {
 
 struct FrameParams;
+struct ShadeParams;
 
 // The persistent ray-kernel CTA (one per SM) exists with 24 and with 28 warps; plan_trace picks per launch.
 struct TracePlan { int threads; int max_slots; };   // threads per CTA; sphere slots resident in shared memory per launch
@@ -26,12 +27,13 @@ cudaError_t launch_trace(cudaStream_t st, int n_ctas, const FrameParams& fp, con
                          const float* g_dmin, const float4* g_cone, const float* g_sin, const int32_t* sphere_obj, int n_spheres,
                          int n_slots, const rtc_object* objs, const int32_t* plane_obj, int n_planes, float* hit_t,
                          int32_t* hit_idx, unsigned int* tile_counter, int carry_in, const float* light /* NULL: primary rays */,
-                         uint8_t* shadow, int threads, bool cull, unsigned long long* groups_tested);
-constexpr float kLightPos[3] = {1.0f, 50.0f, 0.0f};            // the reference's hard-coded light (RayTracing.cu:146)
+                         uint8_t* shadow, int threads, bool cull, unsigned long long* groups_tested,
+                         const ShadeParams& sp, int shade_mode /* >= 0: shade + quantise in the tile epilogue; -1: no */,
+                         uint8_t* color, uint8_t* glyph, bool write_hits);
 
-// kernel 2 (rtc_shade.cu)
-cudaError_t launch_shade(cudaStream_t st, const FrameParams& fp, int mode, uint32_t flags,
-                         const rtc_object* objs, int n_objs, const float* hit_t, const int32_t* hit_idx,
+// kernel 2 (rtc_shade.cu): stand-alone shade + quantise, used only after a shadow pass
+cudaError_t launch_shade(cudaStream_t st, const FrameParams& fp, const ShadeParams& sp, int mode,
+                         const rtc_object* objs, const float* hit_t, const int32_t* hit_idx,
                          const uint8_t* shadow /* NULL: every point is lit */, uint8_t* color, uint8_t* glyph);
 
 cudaError_t launch_ansi256_cube(cudaStream_t st, uint8_t* out /* 2^24 bytes */);
@@ -44,6 +46,9 @@ size_t encode_state_bytes(uint64_t n_cells);
 cudaError_t launch_encode(cudaStream_t st, const uint8_t* color, const uint8_t* glyph, uint32_t x, uint32_t y,
                           int mode, char* out, size_t cap, unsigned long long* total, void* scratch, size_t scratch_bytes,
                           uint32_t parity, bool continues = false /* the cell stored before `color` precedes cell 0 */);
+
+// planes -> the reference's raw 20*x*y-byte cell buffer (compatibility / parity hook; rtc_encode.cu)
+cudaError_t launch_expand_raw(cudaStream_t st, const uint8_t* color, const uint8_t* glyph, uint32_t x, uint32_t y, int mode, char* out);
 
 // physics (rtc_shade.cu)
 cudaError_t launch_update_objects(cudaStream_t st, rtc_object* objs, int n, double dt);

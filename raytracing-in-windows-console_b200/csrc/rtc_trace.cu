@@ -32,6 +32,7 @@
 
 #include "rtc_device.cuh"
 #include "rtc_kernels.h"
+#include "rtc_shade.cuh"
 
 namespace rtc {
 
@@ -74,11 +75,20 @@ hoist_kernel(const rtc_object* __restrict__ objs, const int32_t* __restrict__ sp
         if (cd > 0.0f && cd < 3.0e38f) {
             const float g = RTC_TWO64 / sqrtf(cd);
             gx = ocx * g; gy = ocy * g; gz = ocz * g;
-            // A unit-direction ray from outside meets the sphere no nearer than |oc| - r; the reference's rounded
-            // distance (direction normalised to a few ulp, cancellation in -b - sqrt(disc) of order ulp(|oc|)) stays above
-            // that minus 1e-5 (|oc| + r) with a wide margin (DESIGN.md "reject bound").
-            const float len = sqrtf(oc2), r = fabsf(s.radius);
-            dmin = fmaxf((len - r) - 1.0e-5f * (len + r), 0.0f);
+            // Lower bound of the reference's ROUNDED hit distance over every ray: the minimum over s1 of exact_group's
+            // per-candidate bound t_lb(s1) (same discriminant slack: the rounding error of b*b - 4ac, ~23u|oc|^2, is
+            // amplified by the sqrt, so near-tangent hits of small or distant spheres come out up to ~3e-3|oc| NEARER
+            // than the geometric |oc| - r).  With p = -s1 and K = 3e-6(|oc|^2 + |c|) - c < 0 (implied by c' > 0),
+            // t_lb(p) = p - sqrt(p^2 + K)(1 + 1e-6) - 2e-6(p + |oc|) decreases in p, so its minimum sits at the largest
+            // p a unit direction (to 1e-6) allows, p = |oc|(1 + 1e-6).  Evaluated in binary64, then rounded down.
+            const double L = sqrt((double)oc2) * 1.000001;
+            const double K = 3.0e-6 * ((double)oc2 + fabs((double)c)) - (double)c;
+            const double q = fmax(L * L + K, 0.0);
+            const double lb = (L - sqrt(q) * 1.000001) - 2.0e-6 * (2.0 * L);
+            dmin = fmaxf((float)(lb * (lb >= 0.0 ? 0.999999 : 1.000001)) - 1.0e-30f, 0.0f);
+#ifdef RTC_TEST_R01_GROUP_BOUND   // the round-1 bound (geometric |oc| - r): kept only to show that the regression test bites
+            dmin = fmaxf((sqrtf(oc2) - fabsf(s.radius)) - 1.0e-5f * (sqrtf(oc2) + fabsf(s.radius)), 0.0f);
+#endif
         } else {
             gx = gy = gz = inf;
             dmin = 0.0f;
@@ -136,6 +146,15 @@ constexpr int kTile = 16;           // warp tile = 16 x 16 pixels
 // Shared-memory layout (dynamic): [exact float4 x n_slots][fast 12 B x n_slots][group dmin 4 B x n_slots/4][state]
 // state, each [kRays][blockDim.x]: best_t, best_idx, divTwoA, and the exact ray direction
 // (x, y, z) -- the rare exact path indexes rays dynamically, which registers cannot do.
+struct ShadeCtx {
+    ShadeParams sp;
+    float cam[3];
+    float far_dist;
+    const rtc_object* objs;
+    int mode;
+    int pad_;
+};
+static_assert(sizeof(ShadeCtx) <= 96, "ShadeCtx must fit the 96 bytes set aside in the shared-memory budget");
 struct Smem {
     float4* exact;
     float4* fast;      // 3 float4 per group of 4 spheres
@@ -148,6 +167,7 @@ struct Smem {
     float* dirx;
     float* diry;
     float* dirz;
+    struct ShadeCtx* shade;   // tile epilogue: light / material block, camera, mode (one per CTA)
 };
 __device__ __forceinline__ Smem carve(unsigned char* raw, int n_slots, int n_threads)
 {
@@ -166,6 +186,7 @@ __device__ __forceinline__ Smem carve(unsigned char* raw, int n_slots, int n_thr
     s.dirx = st + 3 * n;
     s.diry = st + 4 * n;
     s.dirz = st + 5 * n;
+    s.shade = reinterpret_cast<ShadeCtx*>(st + 6 * n);
     return s;
 }
 
@@ -223,6 +244,15 @@ __device__ __noinline__ void exact_group(const int32_t* __restrict__ sphere_obj,
             if (oi < s.best_idx[slot]) s.best_idx[slot] = oi;
         }
     }
+}
+
+// Tile epilogue, per ray: shade + quantise (rtc_shade.cuh).  Out of line so that its registers (binary64 pow, IEEE
+// division / square-root sequences) do not weigh on the hot loop; executed only by warps with a hit among 32 rays.
+__device__ __noinline__ uint32_t shade_call(const ShadeCtx* __restrict__ sc, float dx, float dy, float dz, float t, int idx)
+{
+    const int mode = sc->mode;
+    return shade_pixel(mode == RTC_BIT_ASCII || mode == RTC_BIT_PIXEL, mode == RTC_BIT_ASCII || mode == RTC_RGB_ASCII, mode,
+                       sc->sp, sc->objs, v3(sc->cam[0], sc->cam[1], sc->cam[2]), sc->far_dist, v3(dx, dy, dz), t, idx, false);
 }
 
 // One group of 4 spheres (2 packed pairs) against the thread's 8 rays, operand-major: 64 packed ops (128 issue
@@ -296,11 +326,19 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
              const rtc_object* __restrict__ objs, const int32_t* __restrict__ plane_obj, int n_planes,
              float* __restrict__ hit_t, int32_t* __restrict__ hit_idx, unsigned int* __restrict__ tile_counter,
              int carry_in /* 1: continue from hit_t/hit_idx (sphere list chunking) */,
-             float lx, float ly, float lz, uint8_t* __restrict__ shadow, unsigned long long* __restrict__ groups_tested)
+             float lx, float ly, float lz, uint8_t* __restrict__ shadow, unsigned long long* __restrict__ groups_tested,
+             const ShadeParams sp, int shade_mode /* >= 0: shade + quantise into color / glyph in the tile epilogue */,
+             uint8_t* __restrict__ color, uint8_t* __restrict__ glyph, int write_hits)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem s = carve(smem_raw, n_slots, kThreads);
     const int tid = threadIdx.x, lane = tid & 31;
+    if (!SHADOW && tid == 0) {
+        ShadeCtx* sc = s.shade;
+        sc->sp = sp;
+        sc->cam[0] = fp.cam[0]; sc->cam[1] = fp.cam[1]; sc->cam[2] = fp.cam[2];
+        sc->far_dist = fp.far_dist; sc->objs = objs; sc->mode = shade_mode;
+    }
     unsigned int my_groups = 0;                                  // groups of 4 spheres this warp ran the packed test on
 
     // Stage the hoisted sphere list once per CTA (persistent kernel).
@@ -464,20 +502,80 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
             }
         }
 
-        // ---- hit records ------------------------------------------------------------------
+        // ---- hit records (primary pass: only when somebody reads them -- the next sphere chunk, the shadow pass, or
+        //      rtc_frame_hits; shadow pass: the occlusion byte) ---------------------------------------------------
+        if (SHADOW || write_hits) {
 #pragma unroll
-        for (int r = 0; r < kRays; ++r) {
-            const uint32_t row = fp.row0 + ty * kTile + py + 2u * r;
-            if (row < fp.row1 && col < W) {
-                const size_t pix = (size_t)(row - fp.row0) * W + col;
-                const int slot = r * kThreads + tid;
-                if (!SHADOW) {
-                    hit_t[pix] = s.best_t[slot];
-                    hit_idx[pix] = s.best_idx[slot];
-                } else {
-                    const bool occluded = s.best_idx[slot] != -1;
-                    if (!carry_in || occluded) shadow[pix] = occluded ? 1 : 0;
+            for (int r = 0; r < kRays; ++r) {
+                const uint32_t row = fp.row0 + ty * kTile + py + 2u * r;
+                if (row < fp.row1 && col < W) {
+                    const size_t pix = (size_t)(row - fp.row0) * W + col;
+                    const int slot = r * kThreads + tid;
+                    if (!SHADOW) {
+                        hit_t[pix] = s.best_t[slot];
+                        hit_idx[pix] = s.best_idx[slot];
+                    } else {
+                        const bool occluded = s.best_idx[slot] != -1;
+                        if (!carry_in || occluded) shadow[pix] = occluded ? 1 : 0;
+                    }
                 }
+            }
+        }
+
+        // ---- tile epilogue: shade + quantise (replaces the separate shade launch and the 8 B/pixel hit-record round
+        //      trip; direction, distance and object of every ray are still in shared memory) ------------------------
+        if (!SHADOW && shade_mode >= 0) {
+            const bool bit8 = shade_mode == RTC_BIT_ASCII || shade_mode == RTC_BIT_PIXEL;
+            const bool has_gl = shade_mode == RTC_BIT_ASCII || shade_mode == RTC_RGB_ASCII;
+            const uint32_t bpp = bit8 ? 1u : 3u;
+            // The tile's planes are staged in the warp's own div2A runs (dead after the sphere loop; one 128-byte run per
+            // r holds tile rows 2r and 2r+1: colour at py * 16 * bpp, glyphs at 96 + py * 16) and leave as 16-byte
+            // stores -- which is what a peer GPU's memory wants when the band is written over NVLink.
+            const bool fast = (W & 15u) == 0u && ((reinterpret_cast<uintptr_t>(color) | reinterpret_cast<uintptr_t>(glyph)) & 15u) == 0u;
+            __syncwarp();
+#pragma unroll 1
+            for (int r = 0; r < kRays; ++r) {
+                const int slot = r * kThreads + tid;
+                const float t = s.best_t[slot];
+                const int idx = s.best_idx[slot];
+                uint32_t v = (bit8 ? 16u : 0u) | ((uint32_t)' ' << 24);
+                if (t <= fp.far_dist) v = shade_call(s.shade, s.dirx[slot], s.diry[slot], s.dirz[slot], t, idx);
+                const uint32_t row = fp.row0 + ty * kTile + py + 2u * r;
+                if (fast) {
+                    unsigned char* run = reinterpret_cast<unsigned char*>(s.div2A + r * kThreads + (tid & ~31));
+                    unsigned char* pc = run + (py * 16u + px) * bpp;
+                    pc[0] = (unsigned char)v;
+                    if (!bit8) { pc[1] = (unsigned char)(v >> 8); pc[2] = (unsigned char)(v >> 16); }
+                    if (has_gl) run[96u + py * 16u + px] = (unsigned char)(v >> 24);
+                } else if (row < fp.row1 && col < W) {
+                    const size_t pix = (size_t)(row - fp.row0) * W + col;
+                    color[pix * bpp] = (uint8_t)v;
+                    if (!bit8) { color[pix * bpp + 1] = (uint8_t)(v >> 8); color[pix * bpp + 2] = (uint8_t)(v >> 16); }
+                    if (has_gl) glyph[pix] = (uint8_t)(v >> 24);
+                }
+            }
+            if (fast) {                                          // W % 16 == 0: every tile is 16 columns wide
+                __syncwarp();
+                const uint32_t row_t = fp.row0 + ty * kTile;     // first row of the tile
+                const uint32_t parts = bpp;                      // 16-byte pieces per tile row: 3 (RGB) or 1 (index)
+                for (uint32_t i = (uint32_t)lane; i < 16u * parts; i += 32u) {
+                    const uint32_t rho = i / parts, part = i - rho * parts;      // tile row, piece
+                    const uint32_t row = row_t + rho;
+                    if (row < fp.row1) {
+                        const unsigned char* run = reinterpret_cast<const unsigned char*>(s.div2A + (rho >> 1) * kThreads + (tid & ~31));
+                        const uint4 q = *reinterpret_cast<const uint4*>(run + (rho & 1u) * 16u * bpp + part * 16u);
+                        *reinterpret_cast<uint4*>(color + ((size_t)(row - fp.row0) * W + tx * kTile) * bpp + part * 16u) = q;
+                    }
+                }
+                if (has_gl && lane < 16) {
+                    const uint32_t row = row_t + (uint32_t)lane;
+                    if (row < fp.row1) {
+                        const unsigned char* run = reinterpret_cast<const unsigned char*>(s.div2A + (lane >> 1) * kThreads + (tid & ~31));
+                        const uint4 q = *reinterpret_cast<const uint4*>(run + 96u + (lane & 1) * 16u);
+                        *reinterpret_cast<uint4*>(glyph + (size_t)(row - fp.row0) * W + tx * kTile) = q;
+                    }
+                }
+                __syncwarp();                                    // the runs are div2A again in the next tile
             }
         }
     }
@@ -498,7 +596,7 @@ cudaError_t configure_trace()   // per device, once per context
 size_t trace_smem_bytes(int n_slots, int threads)
 {
     return (size_t)n_slots * 28 + (size_t)(((n_slots >> 2) + 3) & ~3) * 24 +     // spheres, per-group bounds (4 + 16 + 4 B),
-           (size_t)threads * (6 * kRays * 4);                                     // best_t, best_idx, div2A, dir x/y/z
+           (size_t)threads * (6 * kRays * 4) + 96;                                // best_t, best_idx, div2A, dir x/y/z; ShadeCtx
 }
 
 // Threads per CTA and sphere slots per launch for a band of `rows` rows.
@@ -516,7 +614,7 @@ TracePlan plan_trace(uint32_t x, uint32_t rows, int n_slots, int n_ctas)
     double best_cost = -1.0;
     for (int w = 28; w >= 24; w -= 4) {                                // ties go to 28 warps
         if (force && atoi(force) != w * 32) continue;
-        const int max_slots = (int)((227 * 1024 - 96 - (long long)w * 32 * (6 * kRays * 4)) / 34) & ~3;
+        const int max_slots = (int)((227 * 1024 - 192 - (long long)w * 32 * (6 * kRays * 4)) / 34) & ~3;
         const int chunks = n_slots <= max_slots ? 1 : (n_slots + max_slots - 1) / max_slots;
         if (chunks > kMaxChunks && w > 24) continue;                   // (the API refuses more chunks than it has tickets for)
         const long long per_wave = (long long)n_ctas * w;
@@ -525,7 +623,7 @@ TracePlan plan_trace(uint32_t x, uint32_t rows, int n_slots, int n_ctas)
         const double cost = waves * w * ((double)(n_slots > 0 ? n_slots : 1) + 40.0 * chunks);
         if (best_cost < 0.0 || cost < best_cost) { best_cost = cost; best.threads = w * 32; best.max_slots = max_slots; }
     }
-    if (best.max_slots == 0) best.max_slots = (int)((227 * 1024 - 96 - (long long)best.threads * (6 * kRays * 4)) / 34) & ~3;
+    if (best.max_slots == 0) best.max_slots = (int)((227 * 1024 - 192 - (long long)best.threads * (6 * kRays * 4)) / 34) & ~3;
     return best;
 }
 
@@ -544,14 +642,16 @@ cudaError_t launch_trace(cudaStream_t st, int n_ctas, const FrameParams& fp, con
                          const float* g_dmin, const float4* g_cone, const float* g_sin, const int32_t* sphere_obj, int n_spheres,
                          int n_slots, const rtc_object* objs, const int32_t* plane_obj, int n_planes, float* hit_t,
                          int32_t* hit_idx, unsigned int* tile_counter, int carry_in, const float* light, uint8_t* shadow,
-                         int threads, bool cull, unsigned long long* groups_tested)
+                         int threads, bool cull, unsigned long long* groups_tested, const ShadeParams& sp, int shade_mode,
+                         uint8_t* color, uint8_t* glyph, bool write_hits)
 {
     const size_t smem = trace_smem_bytes(n_slots, threads);
     const float l0 = light ? light[0] : 0.f, l1 = light ? light[1] : 0.f, l2 = light ? light[2] : 0.f;
 #define RTC_TRACE_LAUNCH(SH, T, C)                                                                                       \
     trace_kernel<SH, T, C><<<n_ctas, T, smem, st>>>(fp, g_fast, g_exact, g_dmin, g_cone, g_sin, sphere_obj, n_spheres,  \
                                                     n_slots, objs, plane_obj, n_planes, hit_t, hit_idx, tile_counter,   \
-                                                    carry_in, l0, l1, l2, shadow, groups_tested)
+                                                    carry_in, l0, l1, l2, shadow, groups_tested, sp, shade_mode, color,  \
+                                                    glyph, write_hits ? 1 : 0)
 #define RTC_TRACE_PICK(T)                                                                                                \
     do {                                                                                                                 \
         if (light) { if (cull) RTC_TRACE_LAUNCH(true, T, true); else RTC_TRACE_LAUNCH(true, T, false); }                 \

@@ -24,7 +24,10 @@ void gpuAssert(int rc, const char* file, int line)
 
 RayTracingManager::RayTracingManager()
 {
-    gpuErrchk(rtc_resize(Scene3D::Context(), (uint32_t)PrintMachine::GetWidth(), (uint32_t)PrintMachine::GetHeight()));
+    SceneBackend* b = Scene3D::Backend();
+    if (b->ctx) gpuErrchk(rtc_resize(b->ctx, (uint32_t)PrintMachine::GetWidth(), (uint32_t)PrintMachine::GetHeight()));
+    if (getenv("RTC_FACADE_SYNC")) m_pipelined = false;
+    if (getenv("RTC_FACADE_NO_CULL")) m_culling = false;
 }
 
 RayTracingManager::~RayTracingManager() {}   // (a frame still in flight is dropped with the context)
@@ -33,7 +36,7 @@ void RayTracingManager::SetRenderingMode(const RenderingMode newRenderMode) { cu
 
 void RayTracingManager::Update(const RayTracingCPUToGPUData& params, const DeviceObjectArray<Object3D*>& objects, double dt)
 {
-    rtc_ctx* ctx = reinterpret_cast<rtc_ctx*>(objects.m_deviceArray);
+    SceneBackend* be = reinterpret_cast<SceneBackend*>(objects.m_deviceArray);
     rtc_params p{};
     const MyMath::Vector4* rows[4] = {&params.inverseVMatrix.row1, &params.inverseVMatrix.row2,
                                       &params.inverseVMatrix.row3, &params.inverseVMatrix.row4};
@@ -48,18 +51,19 @@ void RayTracingManager::Update(const RayTracingCPUToGPUData& params, const Devic
                      (m_fixLaunchLimit ? 0u : RTC_FLAG_UPDATE_REF_LAUNCH_LIMIT);
     const char* stream = nullptr;
     size_t size = 0;
-    m_ctx = ctx;
+    m_backend = be;
+    const rtc_mode mode = (rtc_mode)currentRenderingMode;
     if (m_pipelined) {
-        gpuErrchk(rtc_submit(ctx, &p, (rtc_mode)currentRenderingMode, dt, flags));   // frame k
-        if (m_inFlight) {                                                            // frame k-1
-            gpuErrchk(rtc_collect(ctx, &stream, &size));
+        gpuErrchk(be->mgpu ? rtc_mgpu_submit(be->mgpu, &p, mode, dt, flags) : rtc_submit(be->ctx, &p, mode, dt, flags));   // frame k
+        if (m_inFlight) {                                                                                                // frame k-1
+            gpuErrchk(be->mgpu ? rtc_mgpu_collect(be->mgpu, &stream, &size) : rtc_collect(be->ctx, &stream, &size));
             PrintMachine::SetDataInBackBuffer(stream, size);
         }
         m_inFlight = true;
         return;
     }
     // physics step + trace + shade + ANSI encode + stream to (pinned) host memory
-    gpuErrchk(rtc_update(ctx, &p, (rtc_mode)currentRenderingMode, dt, flags, &stream, &size));
+    gpuErrchk(be->mgpu ? rtc_mgpu_update(be->mgpu, &p, mode, dt, flags, &stream, &size) : rtc_update(be->ctx, &p, mode, dt, flags, &stream, &size));
     PrintMachine::SetDataInBackBuffer(stream, size);             // reference RayTracingManager.cu:150
 }
 
@@ -71,10 +75,11 @@ void RayTracingManager::SetPipelined(bool on)
 
 void RayTracingManager::Flush()
 {
-    if (!m_inFlight || !m_ctx) return;
+    if (!m_inFlight || !m_backend) return;
     const char* stream = nullptr;
     size_t size = 0;
-    gpuErrchk(rtc_collect(reinterpret_cast<rtc_ctx*>(m_ctx), &stream, &size));
+    SceneBackend* be = reinterpret_cast<SceneBackend*>(m_backend);
+    gpuErrchk(be->mgpu ? rtc_mgpu_collect(be->mgpu, &stream, &size) : rtc_collect(be->ctx, &stream, &size));
     PrintMachine::SetDataInBackBuffer(stream, size);
     m_inFlight = false;
 }

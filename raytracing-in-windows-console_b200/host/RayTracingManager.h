@@ -32,20 +32,23 @@ public:
     // Extensions.  Shadows: opt-in shadow rays (not in the reference).  FixLaunchLimit(true): let
     // UpdateObjects move more than 1024 objects (the reference's launch is rejected there).
     void SetShadows(bool on) { m_shadows = on; }
+    // Per-tile sphere culling (RTC_FLAG_CULL): identical frames, far fewer ray-sphere tests.  ON by default -- it is
+    // bit-identical by test (tests/test_gpu_parity.py::test_culling_is_invisible).
     void SetCulling(bool on) { m_culling = on; }
-    // Pipelined sink (rtc_submit / rtc_collect): Update(k) enqueues frame k and hands frame k-1 to PrintMachine, so the
-    // copy of k-1 to the host runs under the kernels of k -- one frame of latency, like the reference's own print
-    // thread behind SetDataInBackBuffer.  Flush() delivers the frame still in flight.
+    // Pipelined sink (rtc_submit / rtc_collect, rtc_mgpu_submit / rtc_mgpu_collect): Update(k) enqueues frame k and hands
+    // frame k-1 to PrintMachine, so the copy of k-1 to the host runs under the kernels of k -- one frame of latency, like
+    // the reference's own print thread behind SetDataInBackBuffer.  ON by default (RTC_FACADE_SYNC=1 or
+    // SetPipelined(false) restore the reference's synchronous hand-over); Flush() delivers the frame still in flight.
     void SetPipelined(bool on);
-    void Flush();      // per-tile sphere culling: identical frames, fewer tests (RTC_FLAG_CULL)
+    void Flush();
     void FixLaunchLimit(bool on) { m_fixLaunchLimit = on; }
 
 private:
     RenderingMode currentRenderingMode = BIT_ASCII;    // reference RayTracingManager.h:53
     bool m_shadows = false;
-    bool m_culling = false;
-    bool m_pipelined = false;
+    bool m_culling = true;
+    bool m_pipelined = true;
     bool m_inFlight = false;
-    void* m_ctx = nullptr;
+    void* m_backend = nullptr;
     bool m_fixLaunchLimit = false;
 };

@@ -1,30 +1,56 @@
 #include "Scene3D.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
+#include <string>
 
 #include "../../include/rtc.h"
 
 namespace {
-rtc_ctx* g_ctx = nullptr;
+SceneBackend g_backend;
+bool g_backend_up = false;
 void check(int rc, const char* what)
 {
     if (rc != RTC_OK) throw std::runtime_error(std::string(what) + ": " + rtc_last_error());
 }
 }  // namespace
 
-rtc_ctx* Scene3D::Context()
+SceneBackend* Scene3D::Backend()
 {
-    if (!g_ctx) {
-        const char* dev = getenv("RTC_DEVICE");
-        check(rtc_create(&g_ctx, dev ? atoi(dev) : 0), "rtc_create");   // throws when no B200 is usable: no CPU fallback
+    if (!g_backend_up) {
+        const char* gpus = getenv("RTC_GPUS");
+        const int n = gpus ? atoi(gpus) : 1;
+        if (n > 1) {
+            int ids[16], n_ids = 0;
+            if (const char* devs = getenv("RTC_DEVICES")) {
+                std::string d(devs);
+                size_t pos = 0;
+                while (n_ids < 16 && pos <= d.size()) {
+                    const size_t comma = d.find(',', pos);
+                    ids[n_ids++] = atoi(d.substr(pos, comma == std::string::npos ? std::string::npos : comma - pos).c_str());
+                    if (comma == std::string::npos) break;
+                    pos = comma + 1;
+                }
+            }
+            const char* ga = getenv("RTC_GATHER");
+            const int gather = (ga && std::string(ga) == "p2p") ? RTC_GATHER_P2P : RTC_GATHER_HOST;
+            check(rtc_mgpu_create(&g_backend.mgpu, n, n_ids == n ? ids : nullptr, gather), "rtc_mgpu_create");
+        } else {
+            const char* dev = getenv("RTC_DEVICE");
+            check(rtc_create(&g_backend.ctx, dev ? atoi(dev) : 0), "rtc_create");   // throws when no B200 is usable: no CPU fallback
+        }
+        g_backend_up = true;
     }
-    return g_ctx;
+    return &g_backend;
 }
+
+rtc_ctx* Scene3D::Context() { return Backend()->ctx; }
 
 void Scene3D::InitEmpty()
 {
-    check(rtc_scene_clear(Context()), "rtc_scene_clear");
+    SceneBackend* b = Backend();
+    check(b->mgpu ? rtc_mgpu_scene_clear(b->mgpu) : rtc_scene_clear(b->ctx), "rtc_scene_clear");
     m_count = m_spheres = m_planes = 0;
 }
 
@@ -48,7 +74,9 @@ void Scene3D::CreateSphere(const float radius, const MyMath::Vector3& middlePos,
         throw std::runtime_error("Error! Out of dedicated memory when trying to create an object.");
     const Sphere s(middlePos, radius, color);        // draws speed from rand() like the reference
     const float c[3] = {middlePos.x, middlePos.y, middlePos.z}, k[3] = {color.x, color.y, color.z};
-    check(rtc_scene_add_sphere(Context(), c, radius, k, s.GetSpeed(), s.GetMover()), "rtc_scene_add_sphere");
+    SceneBackend* b = Backend();
+    check(b->mgpu ? rtc_mgpu_scene_add_sphere(b->mgpu, c, radius, k, s.GetSpeed(), s.GetMover())
+                  : rtc_scene_add_sphere(b->ctx, c, radius, k, s.GetSpeed(), s.GetMover()), "rtc_scene_add_sphere");
     ++m_spheres; ++m_count;
 }
 
@@ -57,7 +85,9 @@ void Scene3D::CreatePlane(const MyMath::Vector3& middlePos, const MyMath::Vector
 {
     if ((size_t)(m_planes + 1) * 96 > FIVE_MEGABYTES) return;
     const float c[3] = {middlePos.x, middlePos.y, middlePos.z}, n[3] = {normal.x, normal.y, normal.z}, k[3] = {color.x, color.y, color.z};
-    check(rtc_scene_add_plane(Context(), c, n, k, width, height), "rtc_scene_add_plane");
+    SceneBackend* b = Backend();
+    check(b->mgpu ? rtc_mgpu_scene_add_plane(b->mgpu, c, n, k, width, height) : rtc_scene_add_plane(b->ctx, c, n, k, width, height),
+          "rtc_scene_add_plane");
     ++m_planes; ++m_count;
 }
 
@@ -65,14 +95,16 @@ void Scene3D::Update(const long double) {}
 
 void Scene3D::CleanUp()
 {
-    if (g_ctx) { rtc_destroy(g_ctx); g_ctx = nullptr; }
+    if (g_backend.mgpu) { rtc_mgpu_destroy(g_backend.mgpu); g_backend.mgpu = nullptr; }
+    if (g_backend.ctx) { rtc_destroy(g_backend.ctx); g_backend.ctx = nullptr; }
+    g_backend_up = false;
     m_count = m_spheres = m_planes = 0;
 }
 
 DeviceObjectArray<Object3D*> Scene3D::GetObjects()
 {
     DeviceObjectArray<Object3D*> a;
-    a.m_deviceArray = reinterpret_cast<Object3D**>(Context());   // opaque: the objects live in the rtc context
+    a.m_deviceArray = reinterpret_cast<Object3D**>(Backend());   // opaque: the objects live in the library
     a.allocatedBytes = m_count * (unsigned)sizeof(rtc_object);
     a.count = m_count;
     return a;

@@ -5,6 +5,14 @@
 #include "Object3D.h"
 
 struct rtc_ctx;
+struct rtc_mgpu;
+
+// What DeviceObjectArray::m_deviceArray points at here: the scene lives in the library, either in one context (one GPU)
+// or replicated by the multi-GPU frame driver (RTC_GPUS > 1).  Exactly one of the two is set.
+struct SceneBackend {
+    rtc_ctx* ctx = nullptr;
+    rtc_mgpu* mgpu = nullptr;
+};
 
 #define FIVE_MEGABYTES 5'000'000
 #define HUNDRED_MEGABYTES 100'000'000
@@ -25,7 +33,10 @@ public:
 
     // Extensions for headless use.
     void InitEmpty();                     // device state only, no default objects
-    static rtc_ctx* Context();            // the process-wide rtc context (device 0 or $RTC_DEVICE)
+    static rtc_ctx* Context();            // the process-wide rtc context (device 0 or $RTC_DEVICE); NULL in multi-GPU mode
+    // The process-wide backend.  Environment: RTC_GPUS=N (N > 1: row bands over N GPUs through rtc_mgpu), RTC_DEVICES="0,1,.."
+    // (device ordinals, may repeat), RTC_GATHER=host|p2p, RTC_DEVICE (single-GPU ordinal).
+    static SceneBackend* Backend();
 
 private:
     unsigned int m_count = 0;

@@ -114,16 +114,17 @@ def camera_params(x, y, pos, rot, pixel_aspect=0.0):
     return _camera_params(x, y, pos, rot, pixel_aspect)
 
 
-def config_camera(name, frame=0, n_frames=120):
+def config_camera(name, frame=0, n_frames=120, camera_fn=None):
     """Cameras of SURVEY 8d.  config1: reference default camera (origin, rot (0,pi,0),
     pixel aspect 0.01).  configs 2-3: pos (0,0,-120), rot (0,pi,0), pixel aspect 1/W.
     config 4: orbit R=120 about the origin, phi_k = pi + 2*pi*k/n_frames."""
+    cam = camera_fn or camera_params               # camera_fn: another restatement of Camera3D with the same signature (the oracle's)
     x, y, n, _, _ = CONFIGS[name]
     if n == 0:
-        return camera_params(x, y, (0.0, 0.0, 0.0), (0.0, np.float32(math.pi), 0.0), 0.0)
+        return cam(x, y, (0.0, 0.0, 0.0), (0.0, np.float32(math.pi), 0.0), 0.0)
     k = 1.0 / float(x - 1)
     if name.startswith("config4"):
         phi = math.pi + 2.0 * math.pi * frame / n_frames
         pos = (120.0 * math.sin(phi), 0.0, 120.0 * math.cos(phi))
-        return camera_params(x, y, pos, (0.0, phi, 0.0), k)
-    return camera_params(x, y, (0.0, 0.0, -120.0), (0.0, np.float32(math.pi), 0.0), k)
+        return cam(x, y, pos, (0.0, phi, 0.0), k)
+    return cam(x, y, (0.0, 0.0, -120.0), (0.0, np.float32(math.pi), 0.0), k)

@@ -31,7 +31,8 @@ def test_facade_exposes_reference_api():
         "RayTracingManager::Update(RayTracingCPUToGPUData const&, DeviceObjectArray<Object3D*> const&, double)",
         "RayTracingManager::SetRenderingMode(RenderingMode)", "RayTracingManager::SetPipelined(bool)", "RayTracingManager::Flush()",
         "PrintMachine::Start(unsigned long, unsigned long)", "PrintMachine::SetDataInBackBuffer(char const*, unsigned long)",
-        "PrintMachine::GetBackBuffer()", "PrintMachine::GetMaxSize()", "PrintMachine::Print()",
+        "PrintMachine::GetBackBuffer()", "PrintMachine::GetMaxSize()", "PrintMachine::Print()", "PrintMachine::TerminateThread()",
+        "RayTracing::RayTrace(dim3 const&, dim3 const&, Object3D**, unsigned int, RayTracingCPUToGPUData const*, char*, RenderingMode)",
     ]:
         assert want in syms, f"facade lacks {want}"
 
@@ -44,13 +45,63 @@ def test_facade_frames_match_reference(golden, tmp_path):
     for mode in range(6):
         got = np.fromfile(tmp_path / f"default_240x64_m{mode}.bin", np.uint8)
         assert np.array_equal(got, golden[f"default_240x64_m{mode}_stream"]), f"mode {mode}"
-    subprocess.check_call([os.path.join(HOST, "facade_test"), str(tmp_path), "engine", "3"])
+    # facade defaults: pipelined sink (rtc_submit / rtc_collect behind RayTracingManager::Update) + per-tile culling
+    subprocess.check_call([os.path.join(HOST, "facade_test"), str(tmp_path), "engine", "4"])
     got = np.fromfile(tmp_path / "engine_240x64_m3.bin", np.uint8)
     assert np.array_equal(got, golden["default_240x64_m3_stream"])
-    # pipelined sink (rtc_submit / rtc_collect behind RayTracingManager::Update) + per-tile culling: same bytes
-    subprocess.check_call([os.path.join(HOST, "facade_test"), str(tmp_path), "pipelined", "4"])
-    got = np.fromfile(tmp_path / "pipelined_240x64_m3.bin", np.uint8)
+    # the reference's synchronous hand-over, brute force: same bytes
+    subprocess.check_call([os.path.join(HOST, "facade_test"), str(tmp_path), "sync", "3"])
+    got = np.fromfile(tmp_path / "sync_240x64_m3.bin", np.uint8)
     assert np.array_equal(got, golden["default_240x64_m3_stream"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gather", ["host", "p2p"])
+def test_facade_on_two_gpus(golden, tmp_path, gather):
+    """RTC_GPUS=2: the reference-facing call RayTracingManager::Update renders through the multi-GPU frame driver
+    (rtc_mgpu_*, two row bands) and lands the reference's bytes in PrintMachine.  Uses two real GPUs when the box has
+    them, two contexts on GPU 0 otherwise."""
+    import torch
+    build_facade()
+    two = torch.cuda.device_count() >= 2
+    env = dict(os.environ, RTC_GPUS="2", RTC_DEVICES="0,1" if two else "0,0", RTC_GATHER=gather)
+    subprocess.check_call([os.path.join(HOST, "facade_test"), str(tmp_path), "engine", "5"], env=env)
+    got = np.fromfile(tmp_path / "engine_240x64_m3.bin", np.uint8)
+    assert np.array_equal(got, golden["default_240x64_m3_stream"])
+    subprocess.check_call([os.path.join(HOST, "facade_test"), str(tmp_path), "sync", "2"], env=env)
+    got = np.fromfile(tmp_path / "sync_240x64_m3.bin", np.uint8)
+    assert np.array_equal(got, golden["default_240x64_m3_stream"])
+
+
+@pytest.mark.gpu
+def test_facade_inner_seam_raw_cells(oracle, tmp_path):
+    """RayTracing::RayTrace (reference RayTracing.h:31-38): the raw 20*x*y-byte cell buffer, byte for byte what the
+    reference's kernels leave in m_deviceResultArray (oracle.trace_raw restates them; pinned in test_oracle_vs_reference)."""
+    from rtc_b200 import scenes
+    build_facade()
+    subprocess.check_call([os.path.join(HOST, "facade_test"), str(tmp_path), "raw"])
+    p = scenes.config_camera("config1_240x64")
+    objs = oracle.update_objects(scenes.default_scene(), 0.0) if False else scenes.default_scene()   # RayTrace runs no physics step
+    for mode in range(6):
+        got = np.fromfile(tmp_path / f"raw_240x64_m{mode}.bin", np.uint8)
+        want = oracle.trace_raw(objs, p, mode)
+        assert got.size == 20 * 240 * 64
+        assert np.array_equal(got, want), f"raw cell buffer differs in mode {mode}"
+
+
+@pytest.mark.gpu
+def test_facade_print_thread(golden, tmp_path):
+    """The reference's print thread (PrintMachine.cpp:257-306) into a file: every printed frame is ESC[H + the stream
+    handed to SetDataInBackBuffer + ESC[m + the two FPS lines."""
+    build_facade()
+    subprocess.check_call([os.path.join(HOST, "facade_test"), str(tmp_path), "print", "6"])
+    data = (tmp_path / "printed.bin").read_bytes()
+    frame = golden["default_240x64_m3_stream"].tobytes()
+    assert data.startswith(b"\x1b[H" + frame + b"\x1b[mRendering FPS: ")
+    parts = data.split(b"\x1b[H")
+    assert parts[0] == b"" and 1 <= len(parts) - 1 <= 6
+    for part in parts[1:]:
+        assert part.startswith(frame + b"\x1b[mRendering FPS: ") and part.rstrip().split(b"\n")[-1].startswith(b"Printing FPS: ")
 
 
 def test_facade_fails_loudly_without_gpu(tmp_path):

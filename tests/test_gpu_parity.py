@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from rtc_b200 import scenes
-from rtc_b200._types import (BIT_ASCII, BIT_PIXEL, FLAG_CULL, FLAG_SHADOWS, FLAG_UPDATE_REF_LAUNCH_LIMIT, MODE_NAMES,
+from rtc_b200._types import (BIT_ASCII, BIT_PIXEL, FLAG_CULL, FLAG_KEEP_HITS, FLAG_SHADOWS, FLAG_UPDATE_REF_LAUNCH_LIMIT, MODE_NAMES,
                              OBJECT_DTYPE, RGB_ASCII, RGB_NORMALS, RGB_PIXEL, SDL, mode_bpp, mode_cell, mode_has_glyph)
 from util import PI32, objs_from_bytes, params_from_bytes, parse_stream
 
@@ -25,8 +25,16 @@ def check_frame(ctx, oracle, objs, p, mode, flags=0, expect_stream=None):
     x, y = p.x, p.y
     n_px = (x - 1) * y
     ctx.set_objects(objs)
+    # the product path: the ray kernel shades in its tile epilogue, hit records never leave the SM
     ctx.render(p, mode, flags)
     stream = ctx.frame_ansi()
+    planes = ctx.frame_color(n_px) if mode != SDL else None
+    # the same frame with the parity hook on: hit records kept; planes and stream must not change
+    ctx.render(p, mode, flags | FLAG_KEEP_HITS)
+    assert np.array_equal(ctx.frame_ansi(), stream), "RTC_FLAG_KEEP_HITS changed the stream"
+    if mode != SDL:
+        c2, g2 = ctx.frame_color(n_px)
+        assert np.array_equal(c2, planes[0]) and (g2 is None or np.array_equal(g2, planes[1])), "RTC_FLAG_KEEP_HITS changed the planes"
     dist, index = ctx.frame_hits(n_px)
     o = oracle.trace_planes(objs, p, mode, flags)
     # --- hit records: bit-exact
@@ -99,10 +107,15 @@ def test_many_spheres_band(ctx, oracle):
     objs = scenes.config_scene("config3_4k_1024")
     p = scenes.config_camera("config3_4k_1024")
     ctx.set_objects(objs)
-    ctx.render(p, RGB_PIXEL)
     n_px = (p.x - 1) * p.y
+    ctx.render(p, RGB_PIXEL)
+    color0, _ = ctx.frame_color(n_px)
+    with pytest.raises(Exception, match="KEEP_HITS"):
+        ctx.frame_hits(n_px)
+    ctx.render(p, RGB_PIXEL, FLAG_KEEP_HITS)
     dist, index = ctx.frame_hits(n_px)
     color, _ = ctx.frame_color(n_px)
+    assert np.array_equal(color, color0)
     W = p.x - 1
     for (r0, r1) in [(0, 4), (1078, 1084), (2150, 2160)]:
         o = oracle.trace_planes(objs, p, RGB_PIXEL, row0=r0, row1=r1)
@@ -400,11 +413,11 @@ def test_culling_is_invisible(ctx, oracle, rtc):
     p = scenes.config_camera("config3_4k_1024")
     n_px = (p.x - 1) * p.y
     ctx.set_objects(objs)
-    ctx.render(p, RGB_PIXEL)
+    ctx.render(p, RGB_PIXEL, FLAG_KEEP_HITS)
     d0, i0 = ctx.frame_hits(n_px)
     s0 = ctx.frame_ansi()
     brute = ctx.timings()["sphere_tests"]
-    ctx.render(p, RGB_PIXEL, FLAG_CULL)
+    ctx.render(p, RGB_PIXEL, FLAG_CULL | FLAG_KEEP_HITS)
     d1, i1 = ctx.frame_hits(n_px)
     s1 = ctx.frame_ansi()
     culled = ctx.timings()["sphere_tests"]
@@ -470,3 +483,56 @@ def test_random_scenes_sweep(ctx, oracle, rtc):
         mode = [RGB_PIXEL, RGB_ASCII, BIT_PIXEL, BIT_ASCII, RGB_NORMALS][case % 5]
         flags = [0, FLAG_CULL, FLAG_SHADOWS, FLAG_CULL | FLAG_SHADOWS][case % 4]
         check_frame(ctx, oracle, objs, p, mode, flags=flags)
+
+
+def test_encoder_state_survives_skipped_launches(ctx, oracle, rtc):
+    """The encoder's group accumulators are zeroed by the PREVIOUS count launch (two parities).  Frames that launch no
+    count kernel (SDL, 1-column consoles, renders that fail validation) must not disturb that: a large frame after an
+    odd number of them used to add onto stale sums (round-1 advisor finding)."""
+    objs = scenes.config_scene("config2_1080p_64")
+    p = rtc.camera_params(401, 150, (0, 0, -120), (0, PI32, 0), 1.0 / 400)      # 60000 cells = 47 tiles (> one 32-tile group)
+    one_col = rtc.camera_params(1, 7, (0, 0, -120), (0, PI32, 0), 1.0)
+    ctx.set_objects(objs)
+    ctx.render(p, RGB_PIXEL)
+    want = ctx.frame_ansi()
+    assert np.array_equal(want, oracle.render(objs, p, RGB_PIXEL))
+    for skipped in ("sdl", "one_column", "bad_mode", "sdl+sdl+sdl"):
+        for _ in range(skipped.count("+") + 1):
+            if skipped.startswith("sdl"):
+                ctx.render(p, SDL)
+                assert ctx.frame_ansi().tobytes() == b"\n" * p.y
+            elif skipped == "one_column":
+                ctx.render(one_col, RGB_PIXEL)
+                assert ctx.frame_ansi().tobytes() == b"\n" * 7
+            else:
+                with pytest.raises(rtc.RtcError):
+                    ctx.render(p, 17)
+        ctx.render(p, RGB_PIXEL)
+        assert np.array_equal(ctx.frame_ansi(), want), f"frame after a skipped encoder launch ({skipped}) differs"
+        ctx.render(p, BIT_ASCII)                                             # and the other cell size, same scratch
+        assert np.array_equal(ctx.frame_ansi(), oracle.render(objs, p, BIT_ASCII))
+
+
+def test_group_reject_bound_tiny_spheres(ctx, oracle, rtc):
+    """Radius-0 and tiny spheres sitting ON a larger surface: the reference's rounded hit distance of a near-tangent hit
+    comes out up to ~3e-3 |oc| nearer than the geometric |oc| - r (rounding of b*b - 4ac amplified by the square root),
+    so the reference sometimes accepts the tiny sphere in front of the big one.  The per-group reject bound must not
+    drop those candidates (round-1 advisor finding: the geometric bound did).  Both camera facings, so that the big
+    sphere is tested before (low Morton code) and after the points."""
+    rng = np.random.default_rng(7)
+    n_pts = 700
+    for facing in (+1.0, -1.0):
+        cam = (0.0, 0.0, 120.0 * facing)
+        cz = -40.0 * facing
+        u = rng.normal(size=(n_pts, 3))
+        u[:, 2] = np.abs(u[:, 2]) * facing                                  # the hemisphere facing the camera
+        u /= np.linalg.norm(u, axis=1, keepdims=True)
+        centers = (np.array([0.0, 0.0, cz]) + 60.0 * u).astype(np.float32)
+        radii = np.where(np.arange(n_pts) % 3 == 0, 0.0, rng.choice([0.01, 0.05, 0.1], n_pts)).astype(np.float32)
+        big = [scenes.make_sphere((0.0, 0.0, cz), 60.0, (200, 40, 40)) for _ in range(4)]
+        pts = [scenes.make_sphere(tuple(float(v) for v in centers[i]), float(radii[i]), (20, 250, 20)) for i in range(n_pts)]
+        objs = np.array(big + pts * 4, OBJECT_DTYPE)                        # x4: packed groups of identical spheres
+        rot = (0.0, 0.0 if facing > 0 else float(PI32), 0.0)
+        p = rtc.camera_params(961, 540, cam, rot, 1.0 / 960)
+        check_frame(ctx, oracle, objs, p, RGB_PIXEL)
+        check_frame(ctx, oracle, objs, p, RGB_PIXEL, flags=FLAG_CULL)

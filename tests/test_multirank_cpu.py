@@ -94,3 +94,23 @@ def test_weighted_bands(rtc):
     # 4K frame on 8 GPUs: 17 tile rows x 240 tiles fit one wave of 148 SMs x 28 warps, 18 do not -> rank 0 keeps 16
     assert multigpu.weighted_bands(2160, 8, 62.0, align=16, wave_units=17) == [(0, 256)] + [(256 + 272 * g, 256 + 272 * (g + 1)) for g in range(7)]
     assert multigpu.weighted_bands(2160, 8, 62.0, align=16)[0] == (0, 208)
+
+
+def test_plan_bands_matches_python_and_tiles_exactly(rtc):
+    """rtc_plan_bands (the C++ band planner the multi-GPU driver uses; host only) tiles [0, y) exactly for any y, n,
+    alignment and encoder deficit, and agrees with the Python restatement in rtc_b200.multigpu."""
+    from rtc_b200 import multigpu
+    rng = np.random.default_rng(3)
+    for _ in range(400):
+        y = int(rng.integers(1, 5000))
+        n = int(rng.integers(1, 9))
+        align = int(rng.choice([1, 16]))
+        deficit = float(rng.choice([0.0, 0.0, rng.uniform(0, 200)]))
+        wave = int(rng.choice([0, 17, 8]))
+        got = rtc.plan_bands(y, n, align, deficit, wave)
+        assert got[0][0] == 0 and got[-1][1] == y and len(got) == n
+        assert all(a <= b for a, b in got) and all(got[g][1] == got[g + 1][0] for g in range(n - 1))
+        assert got == [tuple(b) for b in multigpu.weighted_bands(y, n, deficit, align, wave)], (y, n, align, deficit, wave)
+    assert rtc.plan_bands(2160, 8) == multigpu.bands(2160, 8)
+    with pytest.raises(rtc.RtcError):
+        rtc.plan_bands(100, 0)
