@@ -692,7 +692,7 @@ int rtc_mgpu_submit(rtc_mgpu* m, const rtc_params* p, rtc_mode mode, double dt, 
     FrameSlot& f = m->fr[slot];
     f.x = p->x; f.y = p->y; f.mode = mode;
     // P2P: once a few frames have been timed, give device 0 a smaller band to pay for the encoder
-    if (m->gather == RTC_GATHER_P2P && m->n > 1 && !m->calibrated && !m->user_bands && m->n_col >= 3 && m->n_sub == m->n_col) {
+    if (m->gather == RTC_GATHER_P2P && m->n > 1 && !m->calibrated && !m->user_bands && m->n_col >= 3) {
         const uint32_t rows0 = m->last_rows[1] - m->last_rows[0];
         const float band_ms = m->last_ms[0] - m->last_enc_ms;
         if (rows0 > 0 && band_ms > 0.f) m->deficit_rows = (double)m->last_enc_ms / ((double)band_ms / (double)rows0);
@@ -707,13 +707,13 @@ int rtc_mgpu_submit(rtc_mgpu* m, const rtc_params* p, rtc_mode mode, double dt, 
     if (m->gather == RTC_GATHER_P2P) {
         const int ps = (int)(j % kPlaneSlots);
         const size_t n_px = (size_t)(p->x - 1u) * p->y;
-        const size_t need_c = n_px * rtc::mode_bpp(mode) + 64, need_g = rtc::mode_has_glyph(mode) ? n_px + 64 : 0;
+        const size_t need_c = n_px * 3u + 64, need_g = n_px + 64;     // sized for every rendering mode: modes may alternate frame by frame
         if (need_c > m->plane_color[ps].cap || need_g > m->plane_glyph[ps].cap) {
             if (m->n_sub != m->n_col) return fail(RTC_ERR_INVALID, "the frame grew: collect the frames in flight before submitting a larger one");
             CK(cudaSetDevice(m->w[0].device));
             for (int s = 0; s < kPlaneSlots; ++s) {
                 CK(m->plane_color[s].ensure(need_c));
-                if (need_g) CK(m->plane_glyph[s].ensure(need_g));
+                CK(m->plane_glyph[s].ensure(need_g));
             }
         }
     }
