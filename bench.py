@@ -415,7 +415,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         if rank != 0:
             dist.barrier(group=gloo)                            # rank 0 has finished measuring
-            tt = torch.zeros(2, dtype=torch.float64, device="cuda")
+            tt = torch.zeros(2, dtype=torch.float64, device=torch.device("cuda", local_rank))
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dist.destroy_process_group()
             return
@@ -453,7 +453,8 @@ def run_ours(args):
     ms_per_step = r["ms_per_step"]
     if dist is not None:
         dist.barrier(group=gloo)
-        tt = torch.tensor([ms_per_step, r["e2e_ms"]], dtype=torch.float64, device="cuda")
+        torch.cuda.set_device(local_rank)
+        tt = torch.tensor([ms_per_step, r["e2e_ms"]], dtype=torch.float64, device=torch.device("cuda", local_rank))
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)                # max over ranks (the other ranks time nothing: 0)
         ms_per_step = float(tt[0].item())
     value = frame_rays / (ms_per_step * 1e-3) / 1e6

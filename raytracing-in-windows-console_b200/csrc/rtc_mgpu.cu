@@ -45,6 +45,14 @@ constexpr int kPlaneSlots = 2;     // P2P: frame planes on device 0
 constexpr int kMaxGpus = 16;
 constexpr size_t kFlushBytes = 256u << 20;   // > 126 MB of L2
 
+// The entry points below run on the CALLER's thread and touch several devices; the caller's current device (torch's, for
+// one) must come back unchanged.
+struct DeviceGuard {
+    int dev = -1;
+    DeviceGuard() { if (cudaGetDevice(&dev) != cudaSuccess) { dev = -1; (void)cudaGetLastError(); } }
+    ~DeviceGuard() { if (dev >= 0) cudaSetDevice(dev); }
+};
+
 inline void cpu_relax()
 {
 #if defined(__x86_64__) || defined(__i386__)
@@ -472,6 +480,7 @@ int rtc_mgpu_create(rtc_mgpu** out, int n_gpus, const int* device_ids, int gathe
     *out = nullptr;
     if (n_gpus < 1 || n_gpus > kMaxGpus) return fail(RTC_ERR_INVALID, "n_gpus %d out of range (1..%d)", n_gpus, kMaxGpus);
     if (gather != RTC_GATHER_HOST && gather != RTC_GATHER_P2P) return fail(RTC_ERR_INVALID, "unknown gather mode %d", gather);
+    DeviceGuard guard;
     rtc_mgpu* m = new (std::nothrow) rtc_mgpu();
     if (!m) return fail(RTC_ERR_NOMEM, "out of host memory");
     m->n = n_gpus;
@@ -533,6 +542,7 @@ int rtc_mgpu_create(rtc_mgpu** out, int n_gpus, const int* device_ids, int gathe
 void rtc_mgpu_destroy(rtc_mgpu* m)
 {
     if (!m) return;
+    DeviceGuard guard;
     for (int g = 0; g < m->n; ++g) {
         Worker& w = m->w[g];
         if (w.th.joinable()) {
@@ -655,6 +665,7 @@ int rtc_mgpu_scene_get_objects(rtc_mgpu* m, rtc_object* out, uint32_t cap, uint3
 {
     if (!m) return fail(RTC_ERR_INVALID, "mgpu is NULL");
     if (m->n_sub != m->n_col) return fail(RTC_ERR_INVALID, "frames are in flight: collect them first");
+    DeviceGuard guard;
     const int rc = apply_pending_scene(m);
     if (rc) return rc;
     return rtc_scene_get_objects(m->w[0].ctx, out, cap, n);     // every replica ran the same physics steps
@@ -687,6 +698,7 @@ int rtc_mgpu_submit(rtc_mgpu* m, const rtc_params* p, rtc_mode mode, double dt, 
     if (p->x < 1 || p->y < 1) return fail(RTC_ERR_INVALID, "invalid console size %ux%u", p->x, p->y);
     if ((uint64_t)(p->x - 1u) * p->y >= (1ull << 31)) return fail(RTC_ERR_CAPACITY, "console size too large");
     if (m->n_sub - m->n_col >= kSlots) return fail(RTC_ERR_INVALID, "%d frames are already in flight: rtc_mgpu_collect one first", kSlots);
+    DeviceGuard guard;
     const long long j = m->n_sub;
     const int slot = (int)(j % kSlots);
     FrameSlot& f = m->fr[slot];
