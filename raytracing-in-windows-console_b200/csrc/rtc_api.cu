@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <utility>
@@ -200,8 +201,20 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
     if (record_events) CK(cudaEventRecord(c->ev[0], c->stream));
     const bool cull = (flags & RTC_FLAG_CULL) != 0;
     unsigned long long* stats = reinterpret_cast<unsigned long long*>(c->d_counters.p + rtc::kStatsCounter);   // zeroed by the hoist
+    CK(c->d_kd.ensure(c->objs.size() + 4));
+    // The screen-affine packed filter (rtc_trace.cu) assumes what every camera gives: a near-orthonormal 3x3 inverse view
+    // matrix (its error bound is relative to |w| = |col2 + vx col0 + vy col1|; cancellation between skewed columns would
+    // void it).  Anything else -- the C-ABI accepts arbitrary matrices -- runs the dot-product form of the filter.
+    const rtc::FrameParams fp0 = make_frame(p, row0, row1);
+    bool affine = getenv("RTC_NO_AFFINE") == nullptr;
+    for (int a = 0; a < 3 && affine; ++a)
+        for (int b = a; b < 3; ++b) {
+            const double dot = (double)fp0.m[a] * fp0.m[b] + (double)fp0.m[4 + a] * fp0.m[4 + b] + (double)fp0.m[8 + a] * fp0.m[8 + b];
+            if (!(fabs(dot - (a == b ? 1.0 : 0.0)) < 1.0e-3)) affine = false;
+        }
     CK(rtc::launch_hoist(c->stream, c->d_objs.p, c->d_sphere_obj.p, n_spheres, n_slots, p->cam_pos, c->d_fast.p,
-                         c->d_exact.p, c->d_dmin.p, c->d_cone.p, c->d_sin.p, c->d_counters.p, rtc::kNumCounters));
+                         c->d_exact.p, c->d_dmin.p, c->d_cone.p, c->d_sin.p, c->d_counters.p, rtc::kNumCounters, c->d_kd.p,
+                         (int)c->objs.size(), affine ? fp0.m : nullptr));
 
     c->last_launches++;
     const bool shadows = (flags & RTC_FLAG_SHADOWS) != 0 && mode != RTC_SDL && mode != RTC_RGB_NORMALS;
@@ -217,7 +230,7 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
         CK(c->d_cone_l.ensure(n_slots > 0 ? n_slots / 4 + 4 : 4));
         CK(c->d_sin_l.ensure(n_slots > 0 ? n_slots / 4 + 4 : 4));
         CK(rtc::launch_hoist(c->stream, c->d_objs.p, c->d_sphere_obj.p, n_spheres, n_slots, c->shade.light, c->d_fast_l.p,
-                             c->d_exact_l.p, c->d_dmin_l.p, c->d_cone_l.p, c->d_sin_l.p, c->d_counters.p, 0));
+                             c->d_exact_l.p, c->d_dmin_l.p, c->d_cone_l.p, c->d_sin_l.p, c->d_counters.p, 0, nullptr, 0, nullptr));
         c->last_launches++;
     }
     if (record_events) CK(cudaEventRecord(c->ev[1], c->stream));
@@ -240,7 +253,7 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
                                  c->d_cone.p + s0 / 4, c->d_sin.p + s0 / 4, c->d_sphere_obj.p + s0,
                                  sph, slots, c->d_objs.p, c->d_plane_obj.p, last ? n_planes : 0, c->d_hit_t.p,
                                  c->d_hit_idx.p, c->d_counters.p + ch, ch > 0 ? 1 : 0, nullptr, nullptr, plan.threads, cull, stats,
-                                 c->shade, fused && last ? mode : -1, d_color, d_glyph, !last || keep_hits));
+                                 c->shade, fused && last ? mode : -1, d_color, d_glyph, !last || keep_hits, c->d_kd.p, affine));
             c->last_launches++;
         }
         c->hits_valid = keep_hits;
@@ -255,13 +268,13 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
                                      c->d_dmin_l.p + s0 / 4, c->d_cone_l.p + s0 / 4, c->d_sin_l.p + s0 / 4, c->d_sphere_obj.p + s0, sph, slots,
                                      c->d_objs.p, c->d_plane_obj.p, last ? n_planes : 0,
                                      c->d_hit_t.p, c->d_hit_idx.p, c->d_counters.p + 32 + ch, ch > 0 ? 1 : 0, c->shade.light,
-                                     c->d_shadow.p, plan.threads, cull, stats + 1, c->shade, -1, nullptr, nullptr, false));
+                                     c->d_shadow.p, plan.threads, cull, stats + 1, c->shade, -1, nullptr, nullptr, false, nullptr, false));
                 c->last_launches++;
             }
         }
         if (record_events) CK(cudaEventRecord(c->ev[2], c->stream));
         if (shadows) {
-            CK(rtc::launch_shade(c->stream, fp, c->shade, mode, c->d_objs.p, c->d_hit_t.p, c->d_hit_idx.p, c->d_shadow.p,
+            CK(rtc::launch_shade(c->stream, fp, c->shade, mode, c->d_objs.p, c->d_kd.p, c->d_hit_t.p, c->d_hit_idx.p, c->d_shadow.p,
                                  d_color, d_glyph));
             c->last_launches++;
         }
@@ -344,7 +357,7 @@ void rtc_destroy(rtc_ctx* c)
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     c->d_scene.release(); c->d_fast.release(); c->d_exact.release();
-    c->d_fast_l.release(); c->d_exact_l.release(); c->d_shadow.release(); c->d_dmin.release(); c->d_dmin_l.release();
+    c->d_fast_l.release(); c->d_exact_l.release(); c->d_shadow.release(); c->d_kd.release(); c->d_dmin.release(); c->d_dmin_l.release();
     c->d_cone.release(); c->d_cone_l.release(); c->d_sin.release(); c->d_sin_l.release();
     c->d_hit_t.release(); c->d_hit_idx.release(); c->d_color.release(); c->d_glyph.release(); c->d_out[0].release(); c->d_out[1].release();
     c->d_desc.release(); c->d_counters.release(); c->d_total.release(); c->d_sink.release();

@@ -86,6 +86,7 @@ struct rtc_ctx {
     rtc::DevBuf<float> d_fast_l;    // the same hoist with the light as origin (shadow-ray extension)
     rtc::DevBuf<float4> d_exact_l;
     rtc::DevBuf<uint8_t> d_shadow;  // 1 byte per pixel: occluded
+    rtc::DevBuf<float4> d_kd;       // per object: colour / 255 (hoisted out of the per-pixel shading)
 
     // frame buffers
     rtc::DevBuf<float> d_hit_t;

@@ -23,6 +23,9 @@ __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b);
 __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float dvd(float a, float b) { return __fdiv_rn(a, b); }
 __device__ __forceinline__ float sqt(float a) { return __fsqrt_rn(a); }
+// 1.0f / a.  Both __frcp_rn and __fdiv_rn(1.0f, a) are correctly rounded, hence identical; the reciprocal is the
+// shorter sequence (MUFU.RCP + 3 FMA-pipe ops against 5 + FCHK).
+__device__ __forceinline__ float rcp(float a) { return __frcp_rn(a); }
 
 // MyMath (reference MyMath.h:60-106, MyMath.cu:4-34), left-to-right, un-fused.
 __device__ __forceinline__ V3 vsub(V3 a, V3 b) { return v3(sub(a.x, b.x), sub(a.y, b.y), sub(a.z, b.z)); }
@@ -34,7 +37,33 @@ __device__ __forceinline__ float vdot(V3 a, V3 b) { return add(add(mul(a.x, b.x)
 // Vector3::Normalize_GPU (MyMath.h:139-146): reciprocal length, no zero check.
 __device__ __forceinline__ V3 vnormalize(V3 a)
 {
-    const float inv = dvd(1.0f, sqt(vdot(a, a)));
+    const float inv = rcp(sqt(vdot(a, a)));
+    return v3(mul(a.x, inv), mul(a.y, inv), mul(a.z, inv));
+}
+// fl(1 / fl(sqrt(s))) for s within 128 ulp of 1, by integer arithmetic on the bit pattern -- EXACTLY the value the two
+// correctly rounded operations give (checked for every such s in tests/test_oracle_golden.py::test_unit_rsqrt_formula):
+//   s = 1 + m 2^-23 (m >= 0): sqrt = 1 + (m/2) 2^-23 - tiny -> rounds to 1 + floor(m/2) 2^-23 =: 1 + j 2^-23 (an exact tie
+//       minus tiny rounds down); 1/(1 + j 2^-23) = 1 - 2j 2^-24 + tiny -> rounds to 1 - 2j 2^-24;
+//   s = 1 - k 2^-24 (k > 0):  sqrt = 1 - (k/2) 2^-24 - tiny -> rounds to 1 - ceil(k/2) 2^-24 =: 1 - j 2^-24;
+//       1/(1 - j 2^-24) = 1 + (j/2) 2^-23 + tiny -> rounds to 1 + ceil(j/2) 2^-23.
+// The reference re-normalises vectors that are already normalised (the sphere normal three times, the view vector
+// twice: Sphere.cu:67, RayTracing.cu:129, :56, :150, :57); each pass may move an ulp, so none can be dropped -- but its
+// square root and reciprocal (~17 FMA-pipe instructions) reduce to this.
+__device__ __forceinline__ float rsqrt_near_one_exact(float s)
+{
+    const int m = __float_as_int(s) - 0x3F800000;
+    if (m >= -128 && m <= 128) {
+        const int k = -m;
+        const int bits = m >= 0 ? 0x3F800000 - (m & ~1) : 0x3F800000 + ((((k + 1) >> 1) + 1) >> 1);
+        return __int_as_float(bits);
+    }
+    return rcp(sqt(s));                                          // not a unit vector (degenerate geometry): the general sequence
+}
+// Vector3::Normalize_GPU of a vector that is already of unit length to a few ulp (falls back to the general sequence
+// when it is not): bit-identical to vnormalize.
+__device__ __forceinline__ V3 vnormalize_unit(V3 a)
+{
+    const float inv = rsqrt_near_one_exact(vdot(a, a));
     return v3(mul(a.x, inv), mul(a.y, inv), mul(a.z, inv));
 }
 __device__ __forceinline__ float vlength(V3 a) { return sqt(vdot(a, a)); }
@@ -56,17 +85,25 @@ struct FrameParams {
     uint32_t row0, row1;// band of rows this launch traces
 };
 
-// CalculateInitialDirection (reference RayTracing.cu:9-24), exact.
-__device__ __forceinline__ V3 initial_direction(const FrameParams& p, uint32_t row, uint32_t col)
+// CalculateInitialDirection (reference RayTracing.cu:9-24), exact.  Also hands out the view-space coordinates
+// vx = cx*e1, vy = cy*e2 (:20) and the reciprocal length `inv` of the un-normalised direction w = M (vx, vy, 1, 0) (:22-23):
+// the ray kernel's packed filter works on w = col2 + vx col0 + vy col1 directly (rtc_trace.cu, "screen-affine filter").
+__device__ __forceinline__ V3 initial_direction_ex(const FrameParams& p, uint32_t row, uint32_t col, float& vx, float& vy, float& inv)
 {
     const float cy = dvd(sub(p.fy, (float)(2u * row)), p.fy);          // :16
     const float cx = dvd(sub((float)(2u * col), p.fx), p.fx);          // :17
-    const float vx = mul(cx, p.e1), vy = mul(cy, p.e2);                // :20  (vz = 1, vw = 0)
+    vx = mul(cx, p.e1); vy = mul(cy, p.e2);                            // :20  (vz = 1, vw = 0)
     V3 w;                                                              // Matrix::Mult, MyMath.h:303-311
     w.x = add(add(add(mul(p.m[0], vx), mul(p.m[1], vy)), mul(p.m[2], 1.0f)), mul(p.m[3], 0.0f));
     w.y = add(add(add(mul(p.m[4], vx), mul(p.m[5], vy)), mul(p.m[6], 1.0f)), mul(p.m[7], 0.0f));
     w.z = add(add(add(mul(p.m[8], vx), mul(p.m[9], vy)), mul(p.m[10], 1.0f)), mul(p.m[11], 0.0f));
-    return vnormalize(w);                                              // :23
+    inv = rcp(sqt(vdot(w, w)));                                        // :23  Normalize_GPU, MyMath.h:139-146
+    return v3(mul(w.x, inv), mul(w.y, inv), mul(w.z, inv));
+}
+__device__ __forceinline__ V3 initial_direction(const FrameParams& p, uint32_t row, uint32_t col)
+{
+    float vx, vy, inv;
+    return initial_direction_ex(p, row, col, vx, vy, inv);
 }
 
 // Plane::Trace (reference Plane.cu:38-73), exact.  Returns true on hit and sets t.

@@ -22,18 +22,21 @@ cudaError_t configure_trace();
 size_t trace_smem_bytes(int n_slots, int threads);
 cudaError_t launch_hoist(cudaStream_t st, const rtc_object* objs, const int32_t* sphere_obj, int n_spheres,
                          int n_slots, const float cam[3], float* sph_fast, float4* sph_exact, float* grp_dmin,
-                         float4* grp_cone, float* grp_sin, unsigned int* counters, int n_counters);
+                         float4* grp_cone, float* grp_sin, unsigned int* counters, int n_counters,
+                         float4* obj_kd /* NULL: leave it */, int n_objs,
+                         const float* affine_m /* NULL: dot-product layout; else FrameParams::m: screen-affine layout */);
 cudaError_t launch_trace(cudaStream_t st, int n_ctas, const FrameParams& fp, const float* g_fast, const float4* g_exact,
                          const float* g_dmin, const float4* g_cone, const float* g_sin, const int32_t* sphere_obj, int n_spheres,
                          int n_slots, const rtc_object* objs, const int32_t* plane_obj, int n_planes, float* hit_t,
                          int32_t* hit_idx, unsigned int* tile_counter, int carry_in, const float* light /* NULL: primary rays */,
                          uint8_t* shadow, int threads, bool cull, unsigned long long* groups_tested,
                          const ShadeParams& sp, int shade_mode /* >= 0: shade + quantise in the tile epilogue; -1: no */,
-                         uint8_t* color, uint8_t* glyph, bool write_hits);
+                         uint8_t* color, uint8_t* glyph, bool write_hits, const float4* obj_kd /* per object colour / 255 */,
+                         bool affine /* g_fast is in the screen-affine layout (primary rays only) */);
 
 // kernel 2 (rtc_shade.cu): stand-alone shade + quantise, used only after a shadow pass
 cudaError_t launch_shade(cudaStream_t st, const FrameParams& fp, const ShadeParams& sp, int mode,
-                         const rtc_object* objs, const float* hit_t, const int32_t* hit_idx,
+                         const rtc_object* objs, const float4* obj_kd, const float* hit_t, const int32_t* hit_idx,
                          const uint8_t* shadow /* NULL: every point is lit */, uint8_t* color, uint8_t* glyph);
 
 cudaError_t launch_ansi256_cube(cudaStream_t st, uint8_t* out /* 2^24 bytes */);

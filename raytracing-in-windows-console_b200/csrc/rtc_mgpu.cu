@@ -174,26 +174,32 @@ void set_error(rtc_mgpu* m, int g, int code, const char* what)
     }
 }
 
-// mbind(2) without libnuma: interleave the frame buffer's pages over all NUMA nodes, so that no single socket's memory
-// controllers (or the inter-socket link) take the whole fan-in of N PCIe streams.
-char* alloc_interleaved(size_t bytes)
+// Alternative backings of the pinned frame buffer (experiments, RTC_MGPU_HOSTBUF): anonymous memory that is
+// cudaHostRegister'ed -- "thp": transparent huge pages requested (fewer IOMMU translations for eight concurrent DMA
+// streams); "interleave": pages interleaved over all NUMA nodes (mbind(2) without libnuma).  Measured on this pool's
+// 8-GPU box (one socket, one NUMA node): no gain over cudaHostAlloc -- the fan-in of the eight D2H streams tops out at
+// ~85 GB/s whatever the backing (profiles/r02_d2h_fanin.md), so cudaHostAlloc stays the default.
+char* alloc_anonymous(size_t bytes, bool thp, bool interleave)
 {
     void* p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
     if (p == MAP_FAILED) return nullptr;
+#ifdef MADV_HUGEPAGE
+    if (thp) (void)madvise(p, bytes, MADV_HUGEPAGE);
+#endif
 #ifdef SYS_mbind
-    unsigned long mask[16];
-    memset(mask, 0xff, sizeof mask);
-    // MPOL_INTERLEAVE = 3; nodes that do not exist are rejected by some kernels, so probe the node count first
-    int n_nodes = 0;
-    for (int i = 0; i < 64; ++i) {
-        char path[64];
-        snprintf(path, sizeof path, "/sys/devices/system/node/node%d", i);
-        if (access(path, F_OK) == 0) n_nodes = i + 1;
-    }
-    if (n_nodes > 1) {
-        memset(mask, 0, sizeof mask);
-        for (int i = 0; i < n_nodes; ++i) mask[i / (8 * sizeof(long))] |= 1ul << (i % (8 * sizeof(long)));
-        (void)syscall(SYS_mbind, p, bytes, 3 /* MPOL_INTERLEAVE */, mask, (unsigned long)n_nodes + 1, 0u);
+    if (interleave) {
+        int n_nodes = 0;
+        for (int i = 0; i < 64; ++i) {
+            char path[64];
+            snprintf(path, sizeof path, "/sys/devices/system/node/node%d", i);
+            if (access(path, F_OK) == 0) n_nodes = i + 1;
+        }
+        if (n_nodes > 1) {
+            unsigned long mask[16];
+            memset(mask, 0, sizeof mask);
+            for (int i = 0; i < n_nodes; ++i) mask[i / (8 * sizeof(long))] |= 1ul << (i % (8 * sizeof(long)));
+            (void)syscall(SYS_mbind, p, bytes, 3 /* MPOL_INTERLEAVE */, mask, (unsigned long)n_nodes + 1, 0u);
+        }
     }
 #endif
     return static_cast<char*>(p);
@@ -207,10 +213,10 @@ int ensure_host_frame(rtc_mgpu* m, FrameSlot& f, size_t cap)
         else cudaFreeHost(f.host);
         f.host = nullptr; f.host_cap = 0;
     }
-    const size_t want = (cap + cap / 8 + 4095) & ~(size_t)4095;
-    const char* numa = getenv("RTC_MGPU_NUMA");
-    if (numa && !strcmp(numa, "interleave")) {
-        char* p = alloc_interleaved(want);
+    const size_t want = (cap + cap / 8 + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
+    const char* hb = getenv("RTC_MGPU_HOSTBUF");
+    if (hb && (!strcmp(hb, "interleave") || !strcmp(hb, "thp"))) {
+        char* p = alloc_anonymous(want, !strcmp(hb, "thp"), !strcmp(hb, "interleave"));
         if (p) {
             memset(p, 0, want);                                  // fault the pages in under the interleave policy
             if (cudaHostRegister(p, want, cudaHostRegisterPortable) == cudaSuccess) {

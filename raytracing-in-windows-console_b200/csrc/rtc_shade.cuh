@@ -101,12 +101,13 @@ __device__ __forceinline__ float pow32(float x)
 __device__ __forceinline__ V3 blinn_phong(const ShadeParams& sp, V3 kd, V3 point, V3 view, V3 normal)
 {
     V3 L = vsub(v3(sp.light[0], sp.light[1], sp.light[2]), point);   // :48, light position :146
-    float dist = vlength(L);                                    // :50
-    dist = mul(dist, dist);                                     // :51
-    const float inv = dvd(1.0f, dist);                          // :52
-    L = vnormalize(L);                                          // :54
-    const V3 N = vnormalize(normal);                            // :56
-    const V3 V = vnormalize(view);                              // :57
+    const float len = vlength(L);                               // :50
+    const float dist = mul(len, len);                           // :51
+    const float inv = rcp(dist);                                // :52
+    const float linv = rcp(len);                                // :54  Normalize_GPU recomputes the same length
+    L = v3(mul(L.x, linv), mul(L.y, linv), mul(L.z, linv));
+    const V3 N = vnormalize_unit(normal);                       // :56  (already normalised twice by the caller)
+    const V3 V = vnormalize_unit(view);                         // :57  (already normalised by the caller, :150)
     const float di = clampf_ref(vdot(N, L), 0.0f, 1.0f);        // :60-61
     const float diff = mul(mul(mul(sp.diff_color, di), sp.diff_power), inv);   // :64
     const V3 H = vnormalize(vadd(L, V));                        // :67
@@ -120,17 +121,18 @@ __device__ __forceinline__ V3 blinn_phong(const ShadeParams& sp, V3 kd, V3 point
 
 // One traced pixel -> colour key (RGB modes: R | G << 8 | B << 16; 8-bit modes: xterm-256 index) | glyph << 24.
 //   d: the ray direction (CalculateInitialDirection), t / idx: the accepted hit (idx < 0: none), shadowed: the shadow-ray
-//   extension found an occluder (ambient term only).  `objs` is the 64-byte object array, 16-byte aligned.
+//   extension found an occluder (ambient term only).  `objs` is the 64-byte object array, 16-byte aligned; obj_kd[i] is
+//   object i's colour / 255 (hoist kernel).
 //   (BIT8 / GLYPH follow from `mode`; they are separate arguments so that callers with compile-time modes fold them.)
 __device__ __forceinline__ uint32_t shade_pixel(const bool BIT8, const bool GLYPH, int mode, const ShadeParams& sp,
-                                                const rtc_object* __restrict__ objs, V3 cam, float far_dist, V3 d, float t,
-                                                int idx, bool shadowed)
+                                                const rtc_object* __restrict__ objs, const float4* __restrict__ obj_kd, V3 cam,
+                                                float far_dist, V3 d, float t, int idx, bool shadowed)
 {
     uint32_t c0 = BIT8 ? 16u : 0u, c1 = 0u, c2 = 0u, gl = ' ';       // miss cell: ESC[48;5;<NUL>16m / ESC[48;2;0;0;0m (RayTracing.cu:248, :599)
     const bool hit = t <= far_dist;                                   // RayTracing.cu:508
     if (hit && idx >= 0) {
         const float4* q = reinterpret_cast<const float4*>(objs + idx);
-        const float4 q0 = __ldg(q), q1 = __ldg(q + 1);               // type, centre | colour, radius
+        const float4 q0 = __ldg(q);                                   // type, centre
         V3 n;
         if (__float_as_int(q0.x) == RTC_OBJ_SPHERE) {                 // Sphere.cu:67
             n = vnormalize(vsub(vadd(cam, vscale(d, t)), v3(q0.y, q0.z, q0.w)));
@@ -138,7 +140,7 @@ __device__ __forceinline__ uint32_t shade_pixel(const bool BIT8, const bool GLYP
             const float4 q2 = __ldg(q + 2);                           // Plane.cu:72
             n = v3(q2.x, q2.y, q2.z);
         }
-        n = vnormalize(n);                                            // RayTracing.cu:129
+        n = vnormalize_unit(n);                                       // RayTracing.cu:129
         const float shading_value = add(add(mul(n.x, 1.0f), mul(n.y, 0.0f)), mul(n.z, 0.0f));   // :133
         if (GLYPH) {                                                  // GetASCIICharacter, RayTracing.cu:26-39
             int gi = (int)ceilf(mul(shading_value, 67.0f));
@@ -150,13 +152,14 @@ __device__ __forceinline__ uint32_t shade_pixel(const bool BIT8, const bool GLYP
         if (mode == RTC_RGB_NORMALS) {                                // RayTracing.cu:669-709
             r8 = to_u8(mul(n.x, 255.0f)); g8 = to_u8(mul(n.y, 255.0f)); b8 = to_u8(mul(n.z, 255.0f));
         } else {
-            const V3 kd = vdiv(v3(q1.x, q1.y, q1.z), 255.0f);                              // :144
+            const float4 k4 = __ldg(obj_kd + idx);                                         // :144 colour / 255, hoisted per object
+            const V3 kd = v3(k4.x, k4.y, k4.z);
             const V3 point = vadd(cam, vscale(d, t));                                      // :149
             V3 sh;
             if (shadowed)                                             // extension: occluded -> ambient only
                 sh = vcmul(v3(sp.ambient[0], sp.ambient[1], sp.ambient[2]), kd);
             else
-                sh = blinn_phong(sp, kd, point, vnormalize(vscale(d, -1.0f)), n);          // :143-152
+                sh = blinn_phong(sp, kd, point, vnormalize_unit(vscale(d, -1.0f)), n);     // :143-152 (d is a unit vector: RayTracing.cu:23)
             sh = vscale(sh, 255.0f);                                                       // :154
             r8 = to_u8(minf_ref(255.0f, sh.x));                                            // :157, :527
             g8 = to_u8(minf_ref(255.0f, sh.y));

@@ -39,9 +39,16 @@ namespace rtc {
 // Relative deflation of c for the conservative filter.  A reference hit needs
 // fl(fl(s^2)) >= fl(a*c) with s the un-fused dot product and a = d.d; against the fused,
 // scaled u this is implied by |u| >= 2^128 once c is deflated by >= 30.4 * 2^-24 * |oc|^2
-// (DESIGN.md "filter bound"); 6e-6 leaves > 3x headroom.
-#define RTC_FILTER_EPS 6.0e-6f
+// (DESIGN.md "filter bound"); the screen-affine form of the filter (below) needs 44.6 * 2^-24 = 2.7e-6; 1e-5 leaves
+// 3.7x headroom.
+#define RTC_FILTER_EPS 1.0e-5f
 #define RTC_TWO64 18446744073709551616.0f
+
+// Which packed filter the primary pass will run, and the columns of the inverse view matrix it needs.
+struct HoistBasis {
+    int affine;          // 1: store (A, B, C) = g . (col0, col1, col2) per sphere; 0: store g itself
+    float c0[3], c1[3], c2[3];
+};
 
 // ---- kernel 0: hoist --------------------------------------------------------------------
 // One thread per sphere slot (slots are padded to a multiple of 4).
@@ -54,10 +61,14 @@ __global__ void __launch_bounds__(256)
 hoist_kernel(const rtc_object* __restrict__ objs, const int32_t* __restrict__ sphere_obj, int n_spheres,
              int n_slots, float camx, float camy, float camz, float* __restrict__ sph_fast,
              float4* __restrict__ sph_exact, float* __restrict__ grp_dmin, float4* __restrict__ grp_cone,
-             float* __restrict__ grp_sin, unsigned int* __restrict__ counters, int n_counters)
+             float* __restrict__ grp_sin, unsigned int* __restrict__ counters, int n_counters,
+             float4* __restrict__ obj_kd, int n_objs, const HoistBasis hb)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < n_counters) counters[j] = 0u;     // tile tickets for this frame
+    // per OBJECT: kd = colour / 255 (RayTracing.cu:144 divides per pixel; the quotient only depends on the object)
+    if (obj_kd != nullptr && j < n_objs)
+        obj_kd[j] = make_float4(dvd(objs[j].color[0], 255.0f), dvd(objs[j].color[1], 255.0f), dvd(objs[j].color[2], 255.0f), 0.0f);
     // (no early return: the group minimum below is a warp shuffle; n_slots is a multiple of 4, blockDim of 32)
     float ocx = 0.f, ocy = 0.f, ocz = 0.f, c = 1.f, gx = 0.f, gy = 0.f, gz = 0.f;
     float dmin = 3.0e38f;                     // lower bound of any reference hit distance on this sphere
@@ -73,8 +84,18 @@ hoist_kernel(const rtc_object* __restrict__ objs, const int32_t* __restrict__ sp
         const float cd = fmaf(-RTC_FILTER_EPS, oc2, c);                 // deflated c'
         const float inf = __int_as_float(0x7f800000);
         if (cd > 0.0f && cd < 3.0e38f) {
-            const float g = RTC_TWO64 / sqrtf(cd);
-            gx = ocx * g; gy = ocy * g; gz = ocz * g;
+            if (hb.affine) {
+                // screen-affine filter: (A, B, C) = g . (col0, col1, col2) of the inverse view matrix, g = oc 2^64 / sqrt(c'),
+                // in binary64 and rounded once (stored where the dot-product form keeps gx, gy, gz)
+                const double gs = 18446744073709551616.0 / sqrt((double)cd);
+                const double dx = (double)ocx * gs, dy = (double)ocy * gs, dz = (double)ocz * gs;
+                gx = (float)(dx * (double)hb.c0[0] + dy * (double)hb.c0[1] + dz * (double)hb.c0[2]);
+                gy = (float)(dx * (double)hb.c1[0] + dy * (double)hb.c1[1] + dz * (double)hb.c1[2]);
+                gz = (float)(dx * (double)hb.c2[0] + dy * (double)hb.c2[1] + dz * (double)hb.c2[2]);
+            } else {
+                const float g = RTC_TWO64 / sqrtf(cd);
+                gx = ocx * g; gy = ocy * g; gz = ocz * g;
+            }
             // Lower bound of the reference's ROUNDED hit distance over every ray: the minimum over s1 of exact_group's
             // per-candidate bound t_lb(s1) (same discriminant slack: the rounding error of b*b - 4ac, ~23u|oc|^2, is
             // amplified by the sqrt, so near-tangent hits of small or distant spheres come out up to ~3e-3|oc| NEARER
@@ -151,6 +172,7 @@ struct ShadeCtx {
     float cam[3];
     float far_dist;
     const rtc_object* objs;
+    const float4* kd;
     int mode;
     int pad_;
 };
@@ -252,13 +274,21 @@ __device__ __noinline__ uint32_t shade_call(const ShadeCtx* __restrict__ sc, flo
 {
     const int mode = sc->mode;
     return shade_pixel(mode == RTC_BIT_ASCII || mode == RTC_BIT_PIXEL, mode == RTC_BIT_ASCII || mode == RTC_RGB_ASCII, mode,
-                       sc->sp, sc->objs, v3(sc->cam[0], sc->cam[1], sc->cam[2]), sc->far_dist, v3(dx, dy, dz), t, idx, false);
+                       sc->sp, sc->objs, sc->kd, v3(sc->cam[0], sc->cam[1], sc->cam[2]), sc->far_dist, v3(dx, dy, dz), t, idx, false);
 }
 
-// One group of 4 spheres (2 packed pairs) against the thread's 8 rays, operand-major: 64 packed ops (128 issue
-// cycles) + 3 LDS.128 + one NaN check; measured 4.37 cycles/test against the 4.0 of a pure FFMA2 stream
-// (profiles/r01_microbench.md).
-template <int kThreads>
+// One group of 4 spheres (2 packed pairs) against the thread's 8 rays, operand-major, + 3 LDS.128 + one NaN check.
+//
+// AFFINE = false (shadow rays; primary rays under an ill-conditioned view matrix): u = 2^64 d . g, 3 packed ops per test
+//   pair + the sticky accumulate: 64 packed ops per group; measured 4.37 cycles/test against the 4.0 of a pure FFMA2
+//   stream (profiles/r01_microbench.md).
+// AFFINE = true (primary rays): the SCREEN-AFFINE form of the same filter.  A primary ray's un-normalised direction is
+//   affine in its view-space coordinates, w = col2 + vx col0 + vy col1 (RayTracing.cu:20-22), so
+//       2^64 d . g = (2^64 / |w|) (C + vx A + vy B),   (A, B, C) = g . (col0, col1, col2)  per sphere and frame (hoisted).
+//   A thread's 8 rays share their column, i.e. vx: F = C + vx A is ONE packed op per sphere pair and thread, and a test
+//   is t = F + vy_r B, u = t (2^64 / |w_r|) -- 2 packed ops per pair + the sticky accumulate: 50 packed ops per group
+//   instead of 64.  The operands of the dot-product form (ex, ey, ez) become (vx, vy_r, 2^64 / |w_r|) here.
+template <int kThreads, bool AFFINE>
 __device__ __forceinline__ void test_group(const Smem& s, uint32_t fa, int g, const float (&ex)[kRays], const float (&ey)[kRays],
                                            const float (&ez)[kRays], const int32_t* __restrict__ sphere_obj, int n_slots, int tid)
 {
@@ -266,21 +296,44 @@ __device__ __forceinline__ void test_group(const Smem& s, uint32_t fa, int g, co
     const float4 FX = lds128(fa), FY = lds128(fa + 16u), FZ = lds128(fa + 32u);   // warp-broadcast
     f32x2 u[2][kRays];
     f32x2 acc0 = ZERO2, acc1 = ZERO2;                           // NaN-sticky "something overflowed"
+    if (AFFINE) {
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const f32x2 GX = q ? pack2(FX.z, FX.w) : pack2(FX.x, FX.y);
-        const f32x2 GY = q ? pack2(FY.z, FY.w) : pack2(FY.x, FY.y);
-        const f32x2 GZ = q ? pack2(FZ.z, FZ.w) : pack2(FZ.x, FZ.y);
+        for (int q = 0; q < 2; ++q) {
+            const f32x2 A = q ? pack2(FX.z, FX.w) : pack2(FX.x, FX.y);
+            const f32x2 B = q ? pack2(FY.z, FY.w) : pack2(FY.x, FY.y);
+            const f32x2 C = q ? pack2(FZ.z, FZ.w) : pack2(FZ.x, FZ.y);
+            const f32x2 F = fma2(pack2(ex[0], ex[0]), A, C);                                      // FFMA2 x1 per pair
 #pragma unroll
-        for (int r = 0; r < kRays; ++r) u[q][r] = mul2(pack2(ex[r], ex[r]), GX);             // FMUL2 x8, GX reused
+            for (int r = 0; r < kRays; ++r) u[q][r] = fma2(pack2(ey[r], ey[r]), B, F);            // FFMA2 x8, B and F reused
+        }
 #pragma unroll
-        for (int r = 0; r < kRays; ++r) u[q][r] = fma2(pack2(ey[r], ey[r]), GY, u[q][r]);    // FFMA2 x8, GY reused
+        for (int r = 0; r < kRays; ++r) {                                                         // FMUL2 x16: +-inf <=> candidate
+            const f32x2 S = pack2(ez[r], ez[r]);                                                  // (S reused by the pair of ops)
+            u[0][r] = mul2(u[0][r], S);
+            u[1][r] = mul2(u[1][r], S);
+        }
 #pragma unroll
-        for (int r = 0; r < kRays; ++r) u[q][r] = fma2(pack2(ez[r], ez[r]), GZ, u[q][r]);    // FFMA2 x8: +-inf <=> candidate
+        for (int r = 0; r < kRays; ++r) {                                                         // FFMA2 x16: inf*0 -> NaN, sticky
+            acc0 = fma2(u[0][r], ZERO2, acc0);
+            acc1 = fma2(u[1][r], ZERO2, acc1);
+        }
+    } else {
 #pragma unroll
-        for (int r = 0; r < kRays; ++r) {                                                     // FFMA2 x8: inf*0 -> NaN, sticky
-            if (r & 1) acc1 = fma2(u[q][r], ZERO2, acc1);
-            else acc0 = fma2(u[q][r], ZERO2, acc0);
+        for (int q = 0; q < 2; ++q) {
+            const f32x2 GX = q ? pack2(FX.z, FX.w) : pack2(FX.x, FX.y);
+            const f32x2 GY = q ? pack2(FY.z, FY.w) : pack2(FY.x, FY.y);
+            const f32x2 GZ = q ? pack2(FZ.z, FZ.w) : pack2(FZ.x, FZ.y);
+#pragma unroll
+            for (int r = 0; r < kRays; ++r) u[q][r] = mul2(pack2(ex[r], ex[r]), GX);             // FMUL2 x8, GX reused
+#pragma unroll
+            for (int r = 0; r < kRays; ++r) u[q][r] = fma2(pack2(ey[r], ey[r]), GY, u[q][r]);    // FFMA2 x8, GY reused
+#pragma unroll
+            for (int r = 0; r < kRays; ++r) u[q][r] = fma2(pack2(ez[r], ez[r]), GZ, u[q][r]);    // FFMA2 x8: +-inf <=> candidate
+#pragma unroll
+            for (int r = 0; r < kRays; ++r) {                                                     // FFMA2 x8: inf*0 -> NaN, sticky
+                if (r & 1) acc1 = fma2(u[q][r], ZERO2, acc1);
+                else acc0 = fma2(u[q][r], ZERO2, acc0);
+            }
         }
     }
     float alo, ahi;
@@ -318,7 +371,8 @@ __device__ __forceinline__ void test_group(const Smem& s, uint32_t fa, int g, co
 //   no object.  hit_t / hit_idx are INPUTS here; the output is one byte per pixel in `shadow`.
 // CULL = true (RTC_FLAG_CULL): per warp tile, the groups of 4 spheres whose bounding cone (hoisted) misses the tile's
 //   ray cone are skipped -- results are identical, far fewer tests are executed (the count is reported).
-template <bool SHADOW, int kThreads, bool CULL>
+// AFFINE = true: the screen-affine packed filter (see test_group); primary rays only.
+template <bool SHADOW, int kThreads, bool CULL, bool AFFINE>
 __global__ void __launch_bounds__(kThreads, 1)
 trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float4* __restrict__ g_exact,
              const float* __restrict__ g_dmin, const float4* __restrict__ g_cone, const float* __restrict__ g_sin,
@@ -328,7 +382,7 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
              int carry_in /* 1: continue from hit_t/hit_idx (sphere list chunking) */,
              float lx, float ly, float lz, uint8_t* __restrict__ shadow, unsigned long long* __restrict__ groups_tested,
              const ShadeParams sp, int shade_mode /* >= 0: shade + quantise into color / glyph in the tile epilogue */,
-             uint8_t* __restrict__ color, uint8_t* __restrict__ glyph, int write_hits)
+             uint8_t* __restrict__ color, uint8_t* __restrict__ glyph, int write_hits, const float4* __restrict__ obj_kd)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem s = carve(smem_raw, n_slots, kThreads);
@@ -337,7 +391,7 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
         ShadeCtx* sc = s.shade;
         sc->sp = sp;
         sc->cam[0] = fp.cam[0]; sc->cam[1] = fp.cam[1]; sc->cam[2] = fp.cam[2];
-        sc->far_dist = fp.far_dist; sc->objs = objs; sc->mode = shade_mode;
+        sc->far_dist = fp.far_dist; sc->objs = objs; sc->kd = obj_kd; sc->mode = shade_mode;
     }
     unsigned int my_groups = 0;                                  // groups of 4 spheres this warp ran the packed test on
 
@@ -373,7 +427,8 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
         for (int r = 0; r < kRays; ++r) {
             uint32_t row = fp.row0 + ty * kTile + py + 2u * r;
             if (row >= fp.row1) row = fp.row1 - 1u;
-            V3 d = initial_direction(fp, row, colc);
+            float vx, vy, inv;
+            V3 d = initial_direction_ex(fp, row, colc, vx, vy, inv);
             float bt = 99999999.f;                                        // RayTracing.h:21
             int bi = -1;
             const size_t pix = (size_t)(row - fp.row0) * W + colc;
@@ -391,19 +446,20 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
                         n = vnormalize(vsub(point, v3(ob.center[0], ob.center[1], ob.center[2])));
                     else
                         n = v3(ob.normal[0], ob.normal[1], ob.normal[2]); // Plane.cu:72
-                    n = vnormalize(n);                                    // RayTracing.cu:129
+                    n = vnormalize_unit(n);                               // RayTracing.cu:129
                     const V3 lp = vsub(vadd(point, vscale(n, 1.0e-3f)), o);
                     const float len = vlength(lp);
-                    d = vscale(lp, dvd(1.0f, len));
+                    d = vscale(lp, rcp(len));
                     bt = len;
                 } else {
                     d = v3(0.0f, 0.0f, 0.0f);
                 }
             }
-            ex[r] = d.x * RTC_TWO64; ey[r] = d.y * RTC_TWO64; ez[r] = d.z * RTC_TWO64;
+            if (AFFINE) { ex[r] = vx; ey[r] = vy; ez[r] = inv * RTC_TWO64; }                  // (vx is the same for all 8 rays)
+            else { ex[r] = d.x * RTC_TWO64; ey[r] = d.y * RTC_TWO64; ez[r] = d.z * RTC_TWO64; }
             const int slot = r * kThreads + tid;
             s.dirx[slot] = d.x; s.diry[slot] = d.y; s.dirz[slot] = d.z;
-            s.div2A[slot] = dvd(1.0f, mul(2.0f, vdot(d, d)));             // RayTracing.cu:91,93
+            s.div2A[slot] = rcp(mul(2.0f, vdot(d, d)));                   // RayTracing.cu:91,93
             s.best_t[slot] = bt;
             s.best_idx[slot] = bi;
         }
@@ -426,7 +482,7 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
         if (!CULL) {
             uint32_t fa = fast_base;
 #pragma unroll 2
-            for (int g = 0; g < n_groups; ++g, fa += 48u) test_group<kThreads>(s, fa, g, ex, ey, ez, sphere_obj, n_slots, tid);
+            for (int g = 0; g < n_groups; ++g, fa += 48u) test_group<kThreads, AFFINE>(s, fa, g, ex, ey, ez, sphere_obj, n_slots, tid);
             my_groups += (unsigned int)n_groups;
         } else {
             // Bounding cone of this warp's (active) rays: axis = normalised sum of the directions, cos(theta) = the
@@ -475,11 +531,11 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
                 while (m) {
                     const int g0 = gb + __ffs(m) - 1;
                     m &= m - 1;
-                    test_group<kThreads>(s, fast_base + 48u * (uint32_t)g0, g0, ex, ey, ez, sphere_obj, n_slots, tid);
+                    test_group<kThreads, AFFINE>(s, fast_base + 48u * (uint32_t)g0, g0, ex, ey, ez, sphere_obj, n_slots, tid);
                     if (m) {                                     // a second group back to back: the unroll-by-2 of the brute-force loop
                         const int g1 = gb + __ffs(m) - 1;
                         m &= m - 1;
-                        test_group<kThreads>(s, fast_base + 48u * (uint32_t)g1, g1, ex, ey, ez, sphere_obj, n_slots, tid);
+                        test_group<kThreads, AFFINE>(s, fast_base + 48u * (uint32_t)g1, g1, ex, ey, ez, sphere_obj, n_slots, tid);
                     }
                 }
             }
@@ -585,10 +641,11 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
 cudaError_t configure_trace()   // per device, once per context
 {
     cudaError_t e;
-#define RTC_TRACE_ATTR(SH, T, C)                                                                                             \
-    if ((e = cudaFuncSetAttribute(trace_kernel<SH, T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e
-    RTC_TRACE_ATTR(false, 768, false); RTC_TRACE_ATTR(true, 768, false); RTC_TRACE_ATTR(false, 896, false); RTC_TRACE_ATTR(true, 896, false);
-    RTC_TRACE_ATTR(false, 768, true);  RTC_TRACE_ATTR(true, 768, true);  RTC_TRACE_ATTR(false, 896, true);  RTC_TRACE_ATTR(true, 896, true);
+#define RTC_TRACE_ATTR(SH, T, C, A)                                                                                          \
+    if ((e = cudaFuncSetAttribute(trace_kernel<SH, T, C, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e
+    RTC_TRACE_ATTR(false, 768, false, false); RTC_TRACE_ATTR(true, 768, false, false); RTC_TRACE_ATTR(false, 896, false, false); RTC_TRACE_ATTR(true, 896, false, false);
+    RTC_TRACE_ATTR(false, 768, true, false);  RTC_TRACE_ATTR(true, 768, true, false);  RTC_TRACE_ATTR(false, 896, true, false);  RTC_TRACE_ATTR(true, 896, true, false);
+    RTC_TRACE_ATTR(false, 768, false, true);  RTC_TRACE_ATTR(false, 896, false, true); RTC_TRACE_ATTR(false, 768, true, true);   RTC_TRACE_ATTR(false, 896, true, true);
 #undef RTC_TRACE_ATTR
     return cudaSuccess;
 }
@@ -629,12 +686,22 @@ TracePlan plan_trace(uint32_t x, uint32_t rows, int n_slots, int n_ctas)
 
 cudaError_t launch_hoist(cudaStream_t st, const rtc_object* objs, const int32_t* sphere_obj, int n_spheres,
                          int n_slots, const float cam[3], float* sph_fast, float4* sph_exact, float* grp_dmin,
-                         float4* grp_cone, float* grp_sin, unsigned int* counters, int n_counters)
+                         float4* grp_cone, float* grp_sin, unsigned int* counters, int n_counters, float4* obj_kd, int n_objs,
+                         const float* affine_m /* NULL, or the 12 floats of FrameParams::m: screen-affine layout */)
 {
-    const int n = n_slots > n_counters ? n_slots : n_counters;
+    HoistBasis hb;
+    hb.affine = affine_m != nullptr;
+    for (int i = 0; i < 3; ++i) {
+        hb.c0[i] = affine_m ? affine_m[4 * i + 0] : 0.0f;
+        hb.c1[i] = affine_m ? affine_m[4 * i + 1] : 0.0f;
+        hb.c2[i] = affine_m ? affine_m[4 * i + 2] : 0.0f;
+    }
+    int n = n_slots > n_counters ? n_slots : n_counters;
+    if (obj_kd != nullptr && n_objs > n) n = n_objs;
     if (n <= 0) return cudaSuccess;
     hoist_kernel<<<(n + 255) / 256, 256, 0, st>>>(objs, sphere_obj, n_spheres, n_slots, cam[0], cam[1], cam[2],
-                                                  sph_fast, sph_exact, grp_dmin, grp_cone, grp_sin, counters, n_counters);
+                                                  sph_fast, sph_exact, grp_dmin, grp_cone, grp_sin, counters, n_counters,
+                                                  obj_kd, n_objs, hb);
     return cudaGetLastError();
 }
 
@@ -643,20 +710,22 @@ cudaError_t launch_trace(cudaStream_t st, int n_ctas, const FrameParams& fp, con
                          int n_slots, const rtc_object* objs, const int32_t* plane_obj, int n_planes, float* hit_t,
                          int32_t* hit_idx, unsigned int* tile_counter, int carry_in, const float* light, uint8_t* shadow,
                          int threads, bool cull, unsigned long long* groups_tested, const ShadeParams& sp, int shade_mode,
-                         uint8_t* color, uint8_t* glyph, bool write_hits)
+                         uint8_t* color, uint8_t* glyph, bool write_hits, const float4* obj_kd, bool affine)
 {
     const size_t smem = trace_smem_bytes(n_slots, threads);
     const float l0 = light ? light[0] : 0.f, l1 = light ? light[1] : 0.f, l2 = light ? light[2] : 0.f;
-#define RTC_TRACE_LAUNCH(SH, T, C)                                                                                       \
-    trace_kernel<SH, T, C><<<n_ctas, T, smem, st>>>(fp, g_fast, g_exact, g_dmin, g_cone, g_sin, sphere_obj, n_spheres,  \
-                                                    n_slots, objs, plane_obj, n_planes, hit_t, hit_idx, tile_counter,   \
-                                                    carry_in, l0, l1, l2, shadow, groups_tested, sp, shade_mode, color,  \
-                                                    glyph, write_hits ? 1 : 0)
+#define RTC_TRACE_LAUNCH(SH, T, C, A)                                                                                    \
+    trace_kernel<SH, T, C, A><<<n_ctas, T, smem, st>>>(fp, g_fast, g_exact, g_dmin, g_cone, g_sin, sphere_obj, n_spheres, \
+                                                       n_slots, objs, plane_obj, n_planes, hit_t, hit_idx, tile_counter, \
+                                                       carry_in, l0, l1, l2, shadow, groups_tested, sp, shade_mode, color, \
+                                                       glyph, write_hits ? 1 : 0, obj_kd)
 #define RTC_TRACE_PICK(T)                                                                                                \
     do {                                                                                                                 \
-        if (light) { if (cull) RTC_TRACE_LAUNCH(true, T, true); else RTC_TRACE_LAUNCH(true, T, false); }                 \
-        else       { if (cull) RTC_TRACE_LAUNCH(false, T, true); else RTC_TRACE_LAUNCH(false, T, false); }               \
+        if (light) { if (cull) RTC_TRACE_LAUNCH(true, T, true, false); else RTC_TRACE_LAUNCH(true, T, false, false); }   \
+        else if (affine) { if (cull) RTC_TRACE_LAUNCH(false, T, true, true); else RTC_TRACE_LAUNCH(false, T, false, true); } \
+        else       { if (cull) RTC_TRACE_LAUNCH(false, T, true, false); else RTC_TRACE_LAUNCH(false, T, false, false); } \
     } while (0)
+    if (light && affine) return cudaErrorInvalidValue;           // shadow rays do not come from a pixel grid
     if (threads == 896) RTC_TRACE_PICK(896);
     else if (threads == 768) RTC_TRACE_PICK(768);
     else return cudaErrorInvalidValue;

@@ -189,3 +189,21 @@ def test_encode_planes_equals_raw_minimiser_property(oracle):
         assert np.array_equal(got, want)
 
     check()
+
+
+def test_unit_rsqrt_formula():
+    """csrc/rtc_device.cuh: rsqrt_near_one_exact replaces fl(1 / fl(sqrt(s))) for s within 128 ulp of 1 (the reference
+    re-normalises already-normalised vectors: Sphere.cu:67 -> RayTracing.cu:129 -> :56, :150 -> :57) by integer
+    arithmetic on the bit pattern.  The two IEEE operations (numpy float32 sqrt and divide are correctly rounded) and the
+    formula must agree on every such s."""
+    one = 0x3F800000
+    for m in range(-128, 129):
+        s = np.array([one + m], np.int32).view(np.float32)[0]
+        inv = np.float32(1.0) / np.sqrt(s, dtype=np.float32)
+        want = int(np.array([inv], np.float32).view(np.int32)[0])
+        if m >= 0:
+            got = one - (m & ~1)
+        else:
+            k = -m
+            got = one + ((((k + 1) >> 1) + 1) >> 1)
+        assert got == want, (m, hex(want), hex(got))
