@@ -86,7 +86,13 @@ enum {
     /* Parity hook: also keep the hit records (distance, object index) of every ray for rtc_frame_hits.  Without it
      * the ray kernel shades in its tile epilogue and the records never leave the SM (with RTC_FLAG_SHADOWS they are
      * kept anyway: the shadow pass reads them).                                                                    */
-    RTC_FLAG_KEEP_HITS = 1u << 3
+    RTC_FLAG_KEEP_HITS = 1u << 3,
+    /* RGB_NORMALS only.  The reference converts normal * 255 -- negative for half of the normals -- with a plain
+     * (uint8_t) cast (RayTracing.cu:669-671), which is undefined behaviour: its CUDA build saturates (cvt.rzi.u8.f32:
+     * negative -> 0), its sources compiled for x86 wrap (cvttss2si, low byte).  The default follows the x86 build, the
+     * one every parity fixture of this repository is pinned to; this flag selects the CUDA platform's conversion
+     * (cross-checked against the reference's own kernels on a B200: tests/test_ref_cuda_crosscheck.py).           */
+    RTC_FLAG_NORMALS_SATURATE = 1u << 4
 };
 
 /* == RayTracingCPUToGPUData (reference RayTracingManager.h:9-19) without the vptrs.

@@ -130,6 +130,15 @@ class Oracle:
         self.L.orc_ansi256_range(first, count, _arr(out))
         return out
 
+    def set_light(self, light=None):
+        """The 11 floats of rtc_light, or None for the reference's constants (process-wide state of the checker)."""
+        if light is None:
+            self.L.orc_set_light(None)
+        else:
+            a = np.ascontiguousarray(light, np.float32)
+            assert a.size == 11
+            self.L.orc_set_light(_arr(a))
+
 
 class Reference:
     """Front-end of oracle/_ref/libref_cpu.so: the reference's own code on the CPU."""

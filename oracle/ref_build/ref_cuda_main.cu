@@ -2,7 +2,10 @@
 // unmodified for sm_100 with the vcxproj's flags: -rdc=true --use_fast_math) on a scene file written
 // by bench.py, and reports CUDA-event timings of (a) RayTracingManager::Update (memset + kernels +
 // sync + full-buffer D2H + host minimise) and (b) the RayTrace_* kernel alone.
-//   ref_cuda_sm100 <scene.bin> <frames>
+//   ref_cuda_sm100 <scene.bin> <frames> [dump.raw]
+// With a third argument the raw cell buffer the kernel leaves in m_deviceResultArray (20*x*y bytes, after the
+// reference's own per-frame memset) is written to that file: the cross-check of the new path against the reference's
+// REAL platform (tests/test_ref_cuda_crosscheck.py).
 // scene.bin: u32 n_objs, u32 mode, rtc_params (96 B), rtc_object[n_objs] (64 B each).
 #include "pch.h"
 #define private public
@@ -65,6 +68,18 @@ int main(int argc, char** argv)
         if (it) kernel_ms += ms;
     }
     cudaError_t e = cudaGetLastError();
+    if (argc >= 4) {
+        const size_t bytes = (size_t)20 * p.x * p.y;
+        std::vector<char> raw(bytes);
+        cudaMemset(mgr.m_deviceResultArray, 0, bytes);           // RayTracingManager::ResetDeviceBackBuffer (RayTracingManager.cu:161-165)
+        RayTracing::RayTrace(grid, block, arr.m_deviceArray, arr.count, mgr.m_deviceRayTracingData, mgr.m_deviceResultArray, (RenderingMode)mode);
+        cudaDeviceSynchronize();
+        cudaMemcpy(raw.data(), mgr.m_deviceResultArray, bytes, cudaMemcpyDeviceToHost);
+        FILE* o = fopen(argv[3], "wb");
+        if (!o) { perror(argv[3]); return 2; }
+        fwrite(raw.data(), 1, bytes, o);
+        fclose(o);
+    }
     // (a) the whole Update; for > 1024 objects its UpdateObjects launch is invalid (block = count) --
     // clear the sticky-less launch error first so the reference's own gpuErrchk does not exit on it.
     double update_ms = 0.0;

@@ -117,10 +117,14 @@ static int plane_trace(const rtc_object* pl, v3 o, v3 d, float* dist, v3* nrm)
 }
 
 /* ---- BlinnPhongShading (RayTracing.cu:41-79) with its call-site constants (:143-152) ------- */
+/* The light / material constants of the call site (RayTracing.cu:143-152, :77).  The reference hard-codes them; the
+ * product exposes them (rtc_set_light), so the checker can be told the same values (orc_set_light; NULL = reference). */
+static rtc_light g_light = {{1.0f, 50.0f, 0.0f}, 1.0f, 2000.0f, 1.0f, 3000.0f, {0.2f, 0.2f, 0.2f}, 1.0f};
+
 static v3 blinn_phong(v3 kd, v3 point, v3 view, v3 normal)
 {
-    const v3 light_pos = v3_make(1.0f, 50.0f, 0.0f);            /* :146 */
-    const float diff_power = 2000.0f, spec_power = 3000.0f;     /* :147-148 */
+    const v3 light_pos = v3_make(g_light.pos[0], g_light.pos[1], g_light.pos[2]);   /* :146 */
+    const float diff_power = g_light.diffuse_power, spec_power = g_light.specular_power;   /* :147-148 */
     const v3 ones = v3_make(1.0f, 1.0f, 1.0f);
     v3 L = v3_sub(light_pos, point);                            /* :48 */
     float dist = v3_length(L);                                  /* :50 */
@@ -131,13 +135,13 @@ static v3 blinn_phong(v3 kd, v3 point, v3 view, v3 normal)
     const v3 V = v3_normalize_gpu(view);                        /* :57 */
     const float ndl = v3_dot(N, L);                             /* :60 */
     const float di = clampf(ndl, 0.0f, 1.0f);                   /* :61 */
-    const v3 diffuse = v3_scale(v3_scale(v3_scale(ones, di), diff_power), inv); /* :64 */
+    const v3 diffuse = v3_scale(v3_scale(v3_scale(v3_scale(ones, g_light.diffuse_color), di), diff_power), inv); /* :64 (diffuseColor = 1) */
     const v3 H = v3_normalize_gpu(v3_add(L, V));                /* :67 */
     const float ndh = v3_dot(N, H);                             /* :72 */
     const float si = powf(clampf(ndh, 0.0f, 1.0f), 32.0f);      /* :73 */
-    const v3 specular = v3_scale(v3_scale(v3_scale(ones, si), spec_power), inv); /* :75 */
-    const v3 amb = v3_make(0.2f, 0.2f, 0.2f);                   /* :77 */
-    return v3_add(v3_add(v3_cmul(amb, kd), v3_cmul(diffuse, kd)), v3_cmul(specular, ones)); /* :78 */
+    const v3 specular = v3_scale(v3_scale(v3_scale(v3_scale(ones, g_light.specular_color), si), spec_power), inv); /* :75 (specColor = 1) */
+    const v3 amb = v3_make(g_light.ambient[0], g_light.ambient[1], g_light.ambient[2]);                   /* :77 */
+    return v3_add(v3_add(v3_cmul(amb, kd), v3_cmul(diffuse, kd)), v3_cmul(specular, v3_scale(ones, g_light.object_specular))); /* :78 */
 }
 
 /* ---- RayTrace (RayTracing.cu:81-168) -------------------------------------------------------- */
@@ -157,7 +161,7 @@ typedef struct {
  * which is what lets the GPU hoist the per-sphere terms exactly as for primary rays.)                          */
 static int shadow_blocked(const rtc_object* objs, uint32_t n, v3 point, v3 normal)
 {
-    const v3 light_pos = v3_make(1.0f, 50.0f, 0.0f);
+    const v3 light_pos = v3_make(g_light.pos[0], g_light.pos[1], g_light.pos[2]);
     const v3 lp = v3_sub(v3_add(point, v3_scale(normal, 1.0e-3f)), light_pos);
     const float len = v3_length(lp);
     const v3 d = v3_scale(lp, 1.0f / len);
@@ -208,7 +212,7 @@ static void ray_trace(const rtc_object* objs, uint32_t n, v3 o, v3 d, uint32_t f
     v3 shading = blinn_phong(v3_div(r->color, 255.0f), point,
                              v3_normalize_gpu(v3_scale(d, -1.0f)), r->normal);   /* :143-152 */
     if ((flags & RTC_FLAG_SHADOWS) && shadow_blocked(objs, n, point, r->normal)) {
-        shading = v3_cmul(v3_make(0.2f, 0.2f, 0.2f), v3_div(r->color, 255.0f));  /* ambient term only */
+        shading = v3_cmul(v3_make(g_light.ambient[0], g_light.ambient[1], g_light.ambient[2]), v3_div(r->color, 255.0f));  /* ambient term only */
         r->lit = 0;
     }
     shading = v3_scale(shading, 255.0f);                                         /* :154 */
@@ -650,6 +654,12 @@ ORC_API int orc_blinn_phong(const float kd[3], const float point[3], const float
     const v3 r = blinn_phong(v3_make(kd[0], kd[1], kd[2]), v3_make(point[0], point[1], point[2]),
                              v3_make(view[0], view[1], view[2]), v3_make(nrm[0], nrm[1], nrm[2]));
     out[0] = r.x; out[1] = r.y; out[2] = r.z; return 0;
+}
+ORC_API int orc_set_light(const rtc_light* l)
+{
+    static const rtc_light def = {{1.0f, 50.0f, 0.0f}, 1.0f, 2000.0f, 1.0f, 3000.0f, {0.2f, 0.2f, 0.2f}, 1.0f};
+    g_light = l ? *l : def;
+    return 0;
 }
 ORC_API int orc_ansi256_range(uint32_t first, uint32_t count, uint8_t* out)
 {

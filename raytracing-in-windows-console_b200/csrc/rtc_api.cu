@@ -222,6 +222,7 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
     // hit records are then written only on request.  With shadow rays the records feed the light-origin pass and the
     // stand-alone shade kernel runs after it.
     const bool fused = !shadows && mode != RTC_SDL;
+    const int shade_mode = (mode == RTC_RGB_NORMALS && (flags & RTC_FLAG_NORMALS_SATURATE)) ? rtc::kModeNormalsSaturate : mode;
     const bool keep_hits = (flags & RTC_FLAG_KEEP_HITS) != 0 || shadows;
     if (shadows) {
         CK(c->d_fast_l.ensure(n_slots > 0 ? 3 * (size_t)n_slots : 12));
@@ -253,7 +254,7 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
                                  c->d_cone.p + s0 / 4, c->d_sin.p + s0 / 4, c->d_sphere_obj.p + s0,
                                  sph, slots, c->d_objs.p, c->d_plane_obj.p, last ? n_planes : 0, c->d_hit_t.p,
                                  c->d_hit_idx.p, c->d_counters.p + ch, ch > 0 ? 1 : 0, nullptr, nullptr, plan.threads, cull, stats,
-                                 c->shade, fused && last ? mode : -1, d_color, d_glyph, !last || keep_hits, c->d_kd.p, affine));
+                                 c->shade, fused && last ? shade_mode : -1, d_color, d_glyph, !last || keep_hits, c->d_kd.p, affine));
             c->last_launches++;
         }
         c->hits_valid = keep_hits;

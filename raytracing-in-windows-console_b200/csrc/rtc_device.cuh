@@ -187,4 +187,11 @@ __device__ __forceinline__ uint32_t to_u8(float f)
     return (uint32_t)__float2int_rz(f) & 0xffu;
 }
 
+// The same cast on the reference's CUDA platform: cvt.rzi.u8.f32 saturates (negative -> 0, > 255 -> 255, NaN -> 0).
+__device__ __forceinline__ uint32_t to_u8_sat(float f)
+{
+    if (!(f == f)) return 0u;
+    return (uint32_t)__float2int_rz(fminf(fmaxf(f, 0.0f), 255.0f));
+}
+
 }  // namespace rtc

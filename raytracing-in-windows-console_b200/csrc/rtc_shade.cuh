@@ -119,6 +119,8 @@ __device__ __forceinline__ V3 blinn_phong(const ShadeParams& sp, V3 kd, V3 point
               add(add(mul(sp.ambient[2], kd.z), mul(diff, kd.z)), mul(spec, sp.obj_specular)));
 }
 
+constexpr int kModeNormalsSaturate = 100 + RTC_RGB_NORMALS;   // `mode` of shade_pixel for RGB_NORMALS + RTC_FLAG_NORMALS_SATURATE
+
 // One traced pixel -> colour key (RGB modes: R | G << 8 | B << 16; 8-bit modes: xterm-256 index) | glyph << 24.
 //   d: the ray direction (CalculateInitialDirection), t / idx: the accepted hit (idx < 0: none), shadowed: the shadow-ray
 //   extension found an occluder (ambient term only).  `objs` is the 64-byte object array, 16-byte aligned; obj_kd[i] is
@@ -151,6 +153,8 @@ __device__ __forceinline__ uint32_t shade_pixel(const bool BIT8, const bool GLYP
         uint32_t r8, g8, b8;
         if (mode == RTC_RGB_NORMALS) {                                // RayTracing.cu:669-709
             r8 = to_u8(mul(n.x, 255.0f)); g8 = to_u8(mul(n.y, 255.0f)); b8 = to_u8(mul(n.z, 255.0f));
+        } else if (mode == kModeNormalsSaturate) {                    // RTC_FLAG_NORMALS_SATURATE: the CUDA platform's cast
+            r8 = to_u8_sat(mul(n.x, 255.0f)); g8 = to_u8_sat(mul(n.y, 255.0f)); b8 = to_u8_sat(mul(n.z, 255.0f));
         } else {
             const float4 k4 = __ldg(obj_kd + idx);                                         // :144 colour / 255, hoisted per object
             const V3 kd = v3(k4.x, k4.y, k4.z);

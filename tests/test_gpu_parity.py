@@ -536,3 +536,90 @@ def test_group_reject_bound_tiny_spheres(ctx, oracle, rtc):
         p = rtc.camera_params(961, 540, cam, rot, 1.0 / 960)
         check_frame(ctx, oracle, objs, p, RGB_PIXEL)
         check_frame(ctx, oracle, objs, p, RGB_PIXEL, flags=FLAG_CULL)
+
+
+def test_encoder_full_size_bytes(ctx, oracle, rtc):
+    """Config 5 at full size, every byte: 7681x4320 i.i.d. random RGB (663 MB of stream) against the oracle's serial
+    MinimizeRGB restatement; and the three other cell formats (RGB_ASCII, BIT_PIXEL, BIT_ASCII) on 3841x2160 planes with
+    runs and random glyphs."""
+    import torch
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    cases = [(7681, 4320, RGB_PIXEL, "noise"), (3841, 2160, RGB_ASCII, "runs"), (3841, 2160, BIT_PIXEL, "noise"), (3841, 2160, BIT_ASCII, "runs")]
+    for (x, y, mode, pattern) in cases:
+        W, bpp = x - 1, mode_bpp(mode)
+        g = torch.Generator(device="cuda"); g.manual_seed(5 + mode)
+        if pattern == "noise":
+            keys = torch.randint(0, 256, (W * y * bpp,), dtype=torch.uint8, device="cuda", generator=g)
+        else:                                                         # runs of 1..8 equal cells, as a rendered frame has
+            n_runs = W * y // 3
+            base = torch.randint(0, 256, (n_runs, bpp), dtype=torch.uint8, device="cuda", generator=g)
+            lens = torch.randint(1, 9, (n_runs,), device="cuda", generator=g)
+            keys = torch.repeat_interleave(base, lens, dim=0)[:W * y].contiguous().view(-1)
+            assert keys.numel() == W * y * bpp
+        glyph = None
+        if mode_has_glyph(mode):
+            table = torch.tensor(list(b"  .:#@"), dtype=torch.uint8, device="cuda")
+            glyph = table[torch.randint(0, 6, (W * y,), device="cuda", generator=g)]
+        cap = rtc.encode_capacity(x, y, mode)
+        out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+        total = torch.zeros(1, dtype=torch.int64, device="cuda")
+        ctx.encode(keys.data_ptr(), glyph.data_ptr() if glyph is not None else 0, x, y, mode, out.data_ptr(), cap, total.data_ptr())
+        torch.cuda.synchronize()
+        got = out[:int(total.item())].cpu().numpy()
+        want = oracle.encode_planes(keys.cpu().numpy(), glyph.cpu().numpy() if glyph is not None else None, x, y, mode)
+        assert got.size == want.size and np.array_equal(got, want), (x, y, MODE_NAMES[mode])
+        del out, keys, got, want
+    ctx.set_stream(0)
+
+
+def test_config4_full_size(ctx, oracle):
+    """Config 4 at full size (7681x4320, 4096 spheres = two shared-memory chunks of the sphere list, orbit cameras): three
+    orbit frames, three row windows each -- hit index and distance '==', colour +-1 LSB -- brute force and with per-tile
+    culling; and the culled frame's stream == the brute-force frame's stream."""
+    name = "config4_8k_4096"
+    objs = scenes.config_scene(name)
+    ctx.set_objects(objs)
+    for frame in (0, 37, 95):
+        p = scenes.config_camera(name, frame=frame, n_frames=120)
+        W, y = p.x - 1, p.y
+        n_px = W * y
+        streams = []
+        for flags in (0, FLAG_CULL):
+            ctx.render(p, RGB_PIXEL, flags)
+            streams.append(ctx.frame_ansi())
+            ctx.render(p, RGB_PIXEL, flags | FLAG_KEEP_HITS)
+            dist, index = ctx.frame_hits(n_px)
+            color, _ = ctx.frame_color(n_px)
+            for (r0, r1) in [(0, 2), (y // 2 - 1, y // 2 + 2), (y - 3, y)]:
+                o = oracle.trace_planes(objs, p, RGB_PIXEL, row0=r0, row1=r1, nthreads=16)
+                sl = slice(r0 * W, r1 * W)
+                assert np.array_equal(index[sl], o["index"]), (frame, flags, r0)
+                assert dist[sl].tobytes() == o["dist"].tobytes(), (frame, flags, r0)
+                d = np.abs(color[r0 * W * 3:r1 * W * 3].astype(np.int16) - o["color"].astype(np.int16))
+                assert d.max(initial=0) <= RGB_TOL and (d != 0).sum() <= 2, (frame, flags, r0)
+            del dist, index, color
+        assert np.array_equal(streams[0], streams[1]), f"frame {frame}: culling changed the stream"
+        assert np.array_equal(streams[0][:200000], oracle.encode_planes(ctx.frame_color(n_px)[0], None, p.x, p.y, RGB_PIXEL)[:200000])
+
+
+def test_light_parameters(ctx, oracle, rtc):
+    """rtc_set_light: the reference's hard-coded light / material constants (RayTracing.cu:143-152, :77) as context state.
+    NULL restores them; other values change the frame and agree with the oracle evaluated with the same constants."""
+    objs = scenes.default_scene()
+    p = rtc.camera_params(161, 60, (0, 0, 0), (0, PI32, 0))
+    ctx.set_objects(objs)
+    ctx.set_light(None)
+    ref = np.array(ctx.update(p, RGB_PIXEL, dt=0.0, flags=FLAG_UPDATE_REF_LAUNCH_LIMIT))
+    light = [-20.0, 30.0, 5.0, 1.0, 1500.0, 0.5, 2500.0, 0.1, 0.3, 0.2, 1.0]
+    try:
+        ctx.set_light(light)
+        oracle.set_light(light)
+        for mode, flags in ((RGB_PIXEL, 0), (RGB_ASCII, FLAG_SHADOWS), (BIT_PIXEL, 0)):
+            s = check_frame(ctx, oracle, objs, p, mode, flags=flags)
+            if mode == RGB_PIXEL:
+                assert not np.array_equal(s, ref)
+    finally:
+        ctx.set_light(None)
+        oracle.set_light(None)
+    ctx.set_objects(objs)
+    assert np.array_equal(np.array(ctx.update(p, RGB_PIXEL, dt=0.0, flags=FLAG_UPDATE_REF_LAUNCH_LIMIT)), ref)

@@ -1,0 +1,107 @@
+"""GPU (-m gpu): cross-check against the reference's REAL platform -- its own CUDA kernels, compiled unmodified for sm_100
+by oracle/ref_build (oracle/_ref/ref_cuda_sm100: the vcxproj's flags, -rdc=true --use_fast_math;
+oracle/_ref/ref_cuda_sm100_precise: the same without --use_fast_math, i.e. IEEE operations with nvcc's FMA contraction).
+
+The parity ORACLE of this repository is the reference compiled for the CPU (no contraction, no fast math); this test
+measures how far the reference's GPU builds are from it, on the same scenes, from the raw 20*x*y-byte cell buffer the
+reference kernel leaves in m_deviceResultArray:
+  * RGB within +-1 LSB per channel on all but a sliver of pixels (tolerances written below), hit-mask flips counted;
+  * RGB_NORMALS: which float -> uint8_t conversion the CUDA platform performs on negative normals
+    (RTC_FLAG_NORMALS_SATURATE reproduces it);
+and writes the numbers to gpurun_out/ref_cuda_crosscheck.json for DESIGN.md."""
+import json
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from rtc_b200 import scenes
+from rtc_b200._types import FLAG_NORMALS_SATURATE, RGB_ASCII, RGB_NORMALS, RGB_PIXEL, BIT_PIXEL, mode_bpp, mode_has_glyph
+from util import PI32
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STATS = {}
+
+
+def ref_cuda_raw(exe_name, objs, p, mode, tmp_path):
+    exe = os.path.join(ROOT, "oracle", "_ref", exe_name)
+    if not os.path.exists(exe):
+        pytest.skip("%s not built (needs /root/reference at build time)" % exe_name)
+    scene = tmp_path / "scene.bin"
+    with open(scene, "wb") as f:
+        f.write(struct.pack("<II", len(objs), mode))
+        f.write(bytes(p))
+        f.write(objs.tobytes())
+    raw_path = tmp_path / "dump.raw"
+    r = subprocess.run([exe, str(scene), "1", str(raw_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-400:]
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    return np.fromfile(raw_path, np.uint8), info
+
+
+def compare(ctx, name, exe_name, objs, p, mode, tmp_path, flags=0):
+    from oracle.oracle import planes_from_raw
+    raw, info = ref_cuda_raw(exe_name, objs, p, mode, tmp_path)
+    assert raw.size == 20 * p.x * p.y
+    ref_color, ref_glyph, ref_fg = planes_from_raw(raw, p.x, p.y, mode)
+    n_px = (p.x - 1) * p.y
+    ctx.set_objects(objs)
+    ctx.render(p, mode, flags)
+    color, glyph = ctx.frame_color(n_px)
+    bpp = mode_bpp(mode)
+    a = color.reshape(n_px, bpp).astype(np.int16)
+    b = ref_color.reshape(n_px, bpp).astype(np.int16)
+    d = np.abs(a - b).max(axis=1)
+    # hit mask: a miss cell is colour (0,0,0) [8-bit: index 16] with a blank glyph; a hit pixel can be black only if unlit
+    miss_a = (a == (16 if bpp == 1 else 0)).all(axis=1)
+    miss_b = (b == (16 if bpp == 1 else 0)).all(axis=1)
+    st = {"pixels": int(n_px), "identical": int((d == 0).sum()), "within_1": int((d <= 1).sum()), "max_diff": int(d.max(initial=0)),
+          "off_by_more_than_1": int((d > 1).sum()), "hit_mask_flips": int((miss_a != miss_b).sum()),
+          "ref_stream_bytes": info.get("stream_bytes"), "ours_stream_bytes": int(len(ctx.frame_ansi()))}
+    if mode_has_glyph(mode):
+        st["glyph_differs"] = int((glyph != ref_glyph).sum())
+    STATS["%s/%s" % (name, exe_name)] = st
+    return st
+
+
+@pytest.fixture(scope="module", autouse=True)
+def write_stats():
+    yield
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "ref_cuda_crosscheck.json"), "w") as f:
+        json.dump(STATS, f, indent=1, sort_keys=True)
+
+
+@pytest.mark.parametrize("exe", ["ref_cuda_sm100_precise", "ref_cuda_sm100"])
+def test_rgb_within_one_lsb_of_the_cuda_reference(ctx, rtc, tmp_path, exe):
+    """RGB_PIXEL / RGB_ASCII / BIT_PIXEL on the default scene and on config 2 (1921x1080, 64 spheres + plane).
+    Stated tolerance (north_star): +-1 LSB per channel where FP32 contraction order differs; hit masks identical except on
+    grazing rays.  IEEE build: <= 1e-4 of the pixels may be further than 1 LSB away, <= 1e-5 may flip their hit bit.
+    FastMath build (approximate division, rsqrt, __powf -- not an FP32-contraction difference): reported, bounded loosely."""
+    precise = exe.endswith("precise")
+    cases = [("default_400x150", scenes.default_scene(), scenes.config_camera("config1_400x150")),
+             ("config2_1080p_64", scenes.config_scene("config2_1080p_64"), scenes.config_camera("config2_1080p_64"))]
+    for name, objs, p in cases:
+        for mode, tag in ((RGB_PIXEL, "rgb_pixel"), (RGB_ASCII, "rgb_ascii"), (BIT_PIXEL, "bit_pixel")):
+            st = compare(ctx, "%s/%s" % (name, tag), exe, objs, p, mode, tmp_path)
+            n = st["pixels"]
+            assert st["hit_mask_flips"] <= max(2, 1e-5 * n if precise else 1e-3 * n), st
+            if mode != BIT_PIXEL:                                  # (an xterm index can jump when RGB moves by 1 LSB)
+                assert st["off_by_more_than_1"] <= (1e-4 * n if precise else 0.05 * n), st
+
+
+@pytest.mark.parametrize("exe", ["ref_cuda_sm100_precise", "ref_cuda_sm100"])
+def test_normals_conversion_of_the_cuda_platform(ctx, rtc, tmp_path, exe):
+    """RGB_NORMALS: (uint8_t)(normal * 255) with negative components (RayTracing.cu:669-671).  The CUDA build saturates
+    them to 0; the x86 build wraps.  RTC_FLAG_NORMALS_SATURATE must reproduce the CUDA platform, the default the x86 one."""
+    objs = scenes.default_scene()
+    p = scenes.config_camera("config1_400x150")
+    sat = compare(ctx, "default_400x150/normals_saturate_flag", exe, objs, p, RGB_NORMALS, tmp_path, flags=FLAG_NORMALS_SATURATE)
+    wrap = compare(ctx, "default_400x150/normals_default_wrap", exe, objs, p, RGB_NORMALS, tmp_path)
+    n = sat["pixels"]
+    assert sat["off_by_more_than_1"] <= 1e-3 * n, sat              # the CUDA platform saturates ...
+    assert wrap["off_by_more_than_1"] > 0.01 * n, wrap             # ... and does not wrap (half of all normals have a negative component)
