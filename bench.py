@@ -353,6 +353,7 @@ def measure_mgpu(m, objs, cams, mode, flags, steps, warmup, e2e_steps=None):
     res = {"ms_per_step": float(per_dev.max()) / steps, "per_device_ms": [float(v) / steps for v in per_dev], "bands": info["bands"],
            "encode_ms_on_gpu0": enc / steps}
     n = e2e_steps or steps
+    m.host_stats()                                 # reset the driver's host-side accounting
     m.set_objects(objs)
     m.submit(cam(), mode, 0.0, upd)
     m.set_objects(objs)
@@ -365,6 +366,7 @@ def measure_mgpu(m, objs, cams, mode, flags, steps, warmup, e2e_steps=None):
         nbytes = len(m.collect())                  # frame k: the assembled stream in pinned host memory
     t1 = time.perf_counter()
     m.collect(); m.collect()
+    res["host_us_per_frame"] = m.host_stats()
     res["e2e_ms"] = (t1 - t0) * 1e3 / n
     res["d2h_bytes"] = int(nbytes + 8 * m.n)
     res["h2d_bytes"] = int(objs.nbytes + 96) * m.n
@@ -469,6 +471,8 @@ def run_ours(args):
                    "rtc_mgpu_scene_set_objects + rtc_mgpu_submit / rtc_mgpu_collect (RayTracingManager::Update across %d GPUs, one process, "
                    "three frames in flight), the assembled stream returned in one pinned host buffer" % N),
            "synchronous_update": {"value": mr(r["sync_ms"]), "ms_per_step": r["sync_ms"]}}
+    if "host_us_per_frame" in r:
+        e2e["worker_threads_us_per_frame"] = r["host_us_per_frame"]
 
     pk = peaks()
     sm_count = ctx.device_info()["sm_count"]

@@ -300,6 +300,10 @@ RTC_API int rtc_mgpu_update(rtc_mgpu* m, const rtc_params* params, rtc_mode mode
 /* Of the last collected frame: per-device time of its kernels (CUDA events on each device's stream), the band
  * boundaries rows[0..n_gpus], and (P2P) device 0's encode time.  Any pointer may be NULL.                             */
 RTC_API int rtc_mgpu_last_frame(rtc_mgpu* m, float* device_ms, uint32_t* rows, float* encode_ms);
+/* Host-side accounting since the previous call (idle pipeline only): out[3*g + {0,1,2}] = device g's average microseconds
+ * per frame spent enqueueing (scene staging + launches), waiting for the stream lengths of the devices before it, and in
+ * its D2H copy.                                                                                                       */
+RTC_API int rtc_mgpu_host_stats(rtc_mgpu* m, float* out);
 /* Explicit band boundaries rows[0..n_gpus] for frames of height y (NULL: automatic -- equal bands; in the P2P gather
  * device 0's band shrinks by the measured cost of the encoder).                                                       */
 RTC_API int rtc_mgpu_set_bands(rtc_mgpu* m, uint32_t y, const uint32_t* rows);

@@ -128,7 +128,11 @@ struct Worker {
     cudaEvent_t ev_band[kPlaneSlots] = {};           // P2P: this device's band of the frame in plane slot s has been written
     cudaStream_t copy_stream = nullptr;
     rtc::DevBuf<unsigned char> d_flush;
-    char err[256] = "";
+    // host-side accounting (rtc_mgpu_host_stats): microseconds spent enqueueing frames, from "kernels done" to "copy issued"
+    // (waiting for the lengths of the devices before this one), and from "copy issued" to "copy landed"
+    double us_enqueue = 0.0, us_wait_len = 0.0, us_copy = 0.0;
+    unsigned long long n_frames = 0;
+    std::chrono::steady_clock::time_point t_done, t_issue;
 };
 
 }  // namespace
@@ -363,6 +367,7 @@ bool progress(rtc_mgpu* m, Worker& w)
         f.len[g] = owns_stream ? w.h_total[slot] : 0ull;
         f.len_tag[g].store(j + 1, std::memory_order_release);
         w.stage = 1;
+        w.t_done = std::chrono::steady_clock::now();
         if (!owns_stream) { finish(RTC_OK); return true; }
     }
     if (w.stage == 1) {
@@ -380,11 +385,14 @@ bool progress(rtc_mgpu* m, Worker& w)
         if (e == cudaSuccess) e = cudaEventRecord(w.ev_copy[slot], w.copy_stream);
         if (e != cudaSuccess) { fail(RTC_ERR_CUDA, "D2H of the band stream failed: %s", cudaGetErrorString(e)); finish(RTC_ERR_CUDA); return true; }
         w.stage = 2;
+        w.t_issue = std::chrono::steady_clock::now();
+        w.us_wait_len += std::chrono::duration<double, std::micro>(w.t_issue - w.t_done).count();
     }
     if (w.stage == 2) {
         const cudaError_t q = cudaEventQuery(w.ev_copy[slot]);
         if (q == cudaErrorNotReady) return false;
         if (q != cudaSuccess) { fail(RTC_ERR_CUDA, "D2H of the band stream failed: %s", cudaGetErrorString(q)); finish(RTC_ERR_CUDA); return true; }
+        w.us_copy += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - w.t_issue).count();
         finish(RTC_OK);
     }
     return true;
@@ -404,7 +412,10 @@ void worker_main(rtc_mgpu* m, Worker* w)
         if (have) {
             if (cmd.type == Cmd::QUIT) break;
             const int slot = (int)(cmd.frame % kSlots);
+            const auto tq0 = std::chrono::steady_clock::now();
             int rc = m->failed.load() ? RTC_ERR_CUDA : enqueue_frame(m, *w, cmd);
+            w->us_enqueue += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tq0).count();
+            w->n_frames++;
             if (rc) {                                            // publish the failure so that nobody waits for this band
                 FrameSlot& f = m->fr[slot];
                 if (!m->failed.load()) set_error(m, w->g, rc, rtc_last_error());
@@ -785,6 +796,22 @@ int rtc_mgpu_update(rtc_mgpu* m, const rtc_params* p, rtc_mode mode, double dt, 
     int rc = rtc_mgpu_submit(m, p, mode, dt, flags);
     if (rc) return rc;
     return rtc_mgpu_collect(m, host_ptr, n_bytes);
+}
+
+// Host-side accounting since the last call (idle pipeline only): per device, average microseconds per frame spent
+// enqueueing (scene staging + launches), between "kernels done" and "copy issued", and in the D2H copy.  out[3 * n_gpus].
+int rtc_mgpu_host_stats(rtc_mgpu* m, float* out)
+{
+    if (!m || !out) return fail(RTC_ERR_INVALID, "NULL argument");
+    if (m->n_sub != m->n_col) return fail(RTC_ERR_INVALID, "frames are in flight: collect them first");
+    for (int g = 0; g < m->n; ++g) {
+        Worker& w = m->w[g];
+        if (!wait_for(m, [&] { std::lock_guard<std::mutex> lk(w.mu); return w.q.empty(); })) return fail(RTC_ERR_CUDA, "workers are busy");
+        const double n = w.n_frames ? (double)w.n_frames : 1.0;
+        out[3 * g + 0] = (float)(w.us_enqueue / n); out[3 * g + 1] = (float)(w.us_wait_len / n); out[3 * g + 2] = (float)(w.us_copy / n);
+        w.us_enqueue = w.us_wait_len = w.us_copy = 0.0; w.n_frames = 0;
+    }
+    return RTC_OK;
 }
 
 int rtc_mgpu_last_frame(rtc_mgpu* m, float* device_ms, uint32_t* rows, float* encode_ms)
