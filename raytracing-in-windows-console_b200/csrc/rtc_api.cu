@@ -90,11 +90,31 @@ int upload_scene(rtc_ctx* c)
     const size_t n = c->objs.size();
     c->sphere_obj.clear();
     c->plane_obj.clear();
-    for (size_t i = 0; i < n; ++i) {
-        if (c->objs[i].type == RTC_OBJ_SPHERE) c->sphere_obj.push_back((int32_t)i);
-        else if (c->objs[i].type == RTC_OBJ_PLANE) c->plane_obj.push_back((int32_t)i);
+    // The Morton order only depends on which objects are spheres and where their centres are: a scene that is uploaded
+    // again with the same geometry (per-frame uploads of a static or colour-animated scene) keeps its order.
+    bool same_geometry = c->order_key.size() == 4 * n;
+    for (size_t i = 0; i < n && same_geometry; ++i) {
+        const rtc_object& o = c->objs[i];
+        const float* k = &c->order_key[4 * i];
+        same_geometry = memcmp(k, o.center, 12) == 0 && k[3] == (float)o.type;
     }
-    morton_order(c->objs, c->sphere_obj);
+    if (same_geometry && n > 0) {
+        c->sphere_obj = c->sphere_order;
+        c->plane_obj = c->plane_order;
+    } else {
+        for (size_t i = 0; i < n; ++i) {
+            if (c->objs[i].type == RTC_OBJ_SPHERE) c->sphere_obj.push_back((int32_t)i);
+            else if (c->objs[i].type == RTC_OBJ_PLANE) c->plane_obj.push_back((int32_t)i);
+        }
+        morton_order(c->objs, c->sphere_obj);
+        c->order_key.resize(4 * n);
+        for (size_t i = 0; i < n; ++i) {
+            memcpy(&c->order_key[4 * i], c->objs[i].center, 12);
+            c->order_key[4 * i + 3] = (float)c->objs[i].type;
+        }
+        c->sphere_order = c->sphere_obj;
+        c->plane_order = c->plane_obj;
+    }
     const size_t n_slots = (c->sphere_obj.size() + 3) & ~(size_t)3;
     CK(c->d_fast.ensure(n_slots > 0 ? 3 * n_slots : 12));
     CK(c->d_cone.ensure(n_slots > 0 ? n_slots / 4 + 4 : 4));

@@ -72,6 +72,8 @@ struct rtc_ctx {
     // scene (host master copy + device mirror)
     std::vector<rtc_object> objs;
     std::vector<int32_t> sphere_obj, plane_obj;
+    std::vector<int32_t> sphere_order, plane_order;   // the index lists of the last upload ...
+    std::vector<float> order_key;                     // ... and the geometry they were built from (centre, type per object)
     bool scene_dirty = true;       // host -> device upload pending
     bool host_stale = false;       // device physics ran; host copy must be refreshed before use
     // device scene: ONE blob [objects | sphere index list | plane index list] so that an upload is a single copy

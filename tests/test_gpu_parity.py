@@ -13,7 +13,7 @@ import pytest
 from rtc_b200 import scenes
 from rtc_b200._types import (BIT_ASCII, BIT_PIXEL, FLAG_CULL, FLAG_KEEP_HITS, FLAG_SHADOWS, FLAG_UPDATE_REF_LAUNCH_LIMIT, MODE_NAMES,
                              OBJECT_DTYPE, RGB_ASCII, RGB_NORMALS, RGB_PIXEL, SDL, mode_bpp, mode_cell, mode_has_glyph)
-from util import PI32, objs_from_bytes, params_from_bytes, parse_stream
+from util import PI32, bind_stream, objs_from_bytes, params_from_bytes, parse_stream, unbind_stream
 
 pytestmark = pytest.mark.gpu
 
@@ -146,7 +146,7 @@ def test_trace_band_matches_full_frame(ctx, rtc):
         bpp = mode_bpp(mode)
         color = torch.zeros(W * y * bpp, dtype=torch.uint8, device="cuda")
         glyph = torch.zeros(W * y, dtype=torch.uint8, device="cuda")
-        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        bind_stream(ctx)
         for (r0, r1) in [(0, 67), (67, 135), (135, 136), (136, 270)]:      # ragged bands
             ctx.trace_band(p, mode, r0, r1, color.data_ptr() + r0 * W * bpp, glyph.data_ptr() + r0 * W)
         cap = rtc.encode_capacity(x, y, mode)
@@ -154,7 +154,7 @@ def test_trace_band_matches_full_frame(ctx, rtc):
         total = torch.zeros(1, dtype=torch.int64, device="cuda")
         ctx.encode(color.data_ptr(), glyph.data_ptr() if mode_has_glyph(mode) else 0, x, y, mode, out.data_ptr(), cap, total.data_ptr())
         torch.cuda.synchronize()
-        ctx.set_stream(0)
+        unbind_stream(ctx)
         assert np.array_equal(color.cpu().numpy(), full_color)
         n = int(total.item())
         assert np.array_equal(out[:n].cpu().numpy(), want)
@@ -165,7 +165,7 @@ def test_encoder_edge_cases(ctx, oracle, rtc):
     slice/tile boundaries (160-cell warp slices, 1280-cell tiles), unaligned plane pointers."""
     import torch
     rng = np.random.default_rng(11)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    bind_stream(ctx)
     cases = [(2, 1), (2, 9), (3, 3), (5, 2), (6, 7), (18, 5), (161, 1), (162, 3), (321, 7), (1281, 1), (1282, 2), (2049, 1),
              (2562, 2), (4097, 3), (700, 37), (1025, 16)]
     for (x, y) in cases:
@@ -197,7 +197,7 @@ def test_encoder_edge_cases(ctx, oracle, rtc):
                     got = out[(off % 3):(off % 3) + n].cpu().numpy()
                     want = oracle.encode_planes(keys, glyph, x, y, mode)
                     assert np.array_equal(got, want), (x, y, MODE_NAMES[mode], pattern, off)
-    ctx.set_stream(0)
+    unbind_stream(ctx)
 
 
 def test_encoder_full_size_properties(ctx, oracle, rtc):
@@ -211,10 +211,10 @@ def test_encoder_full_size_properties(ctx, oracle, rtc):
     cap = rtc.encode_capacity(x, y, RGB_PIXEL)
     out = torch.empty(cap, dtype=torch.uint8, device="cuda")
     total = torch.zeros(1, dtype=torch.int64, device="cuda")
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    bind_stream(ctx)
     ctx.encode(rgb.data_ptr(), 0, x, y, RGB_PIXEL, out.data_ptr(), cap, total.data_ptr())
     torch.cuda.synchronize()
-    ctx.set_stream(0)
+    unbind_stream(ctx)
     n = int(total.item())
     px = rgb.view(-1, 3)
     full = torch.ones(W * y, dtype=torch.bool, device="cuda")
@@ -366,7 +366,7 @@ def test_band_encode_concatenates(ctx, rtc):
     p = rtc.camera_params(x, y, (0, 0, -120), (0, PI32, 0), 1.0 / (x - 1))
     W = x - 1
     ctx.set_objects(objs)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    bind_stream(ctx)
     for mode in (RGB_PIXEL, RGB_ASCII, BIT_ASCII, BIT_PIXEL):
         ctx.render(p, mode)
         want = ctx.frame_ansi()
@@ -386,7 +386,7 @@ def test_band_encode_concatenates(ctx, rtc):
             torch.cuda.synchronize()
             pieces.append(out[:int(total.item())].cpu().numpy())
         assert np.array_equal(np.concatenate(pieces), want), MODE_NAMES[mode]
-    ctx.set_stream(0)
+    unbind_stream(ctx)
 
 
 def test_culling_is_invisible(ctx, oracle, rtc):
@@ -430,7 +430,7 @@ def test_quantisers_exhaustive(ctx, oracle, rtc):
     NUL-padded decimal digits of all 256 byte values in every channel position (encoder), against the oracle (which
     tests/test_oracle_vs_reference.py pins exhaustively against the reference)."""
     import torch
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    bind_stream(ctx)
     cube = torch.empty(1 << 24, dtype=torch.uint8, device="cuda")
     ctx.ansi256_cube(cube.data_ptr())
     torch.cuda.synchronize()
@@ -451,7 +451,7 @@ def test_quantisers_exhaustive(ctx, oracle, rtc):
         torch.cuda.synchronize()
         got = out[:int(total.item())].cpu().numpy()
         assert np.array_equal(got, oracle.encode_planes(keys, glyph, x, y, mode)), MODE_NAMES[mode]
-    ctx.set_stream(0)
+    unbind_stream(ctx)
 
 
 def test_random_scenes_sweep(ctx, oracle, rtc):
@@ -543,7 +543,7 @@ def test_encoder_full_size_bytes(ctx, oracle, rtc):
     MinimizeRGB restatement; and the three other cell formats (RGB_ASCII, BIT_PIXEL, BIT_ASCII) on 3841x2160 planes with
     runs and random glyphs."""
     import torch
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    bind_stream(ctx)
     cases = [(7681, 4320, RGB_PIXEL, "noise"), (3841, 2160, RGB_ASCII, "runs"), (3841, 2160, BIT_PIXEL, "noise"), (3841, 2160, BIT_ASCII, "runs")]
     for (x, y, mode, pattern) in cases:
         W, bpp = x - 1, mode_bpp(mode)
@@ -569,7 +569,7 @@ def test_encoder_full_size_bytes(ctx, oracle, rtc):
         want = oracle.encode_planes(keys.cpu().numpy(), glyph.cpu().numpy() if glyph is not None else None, x, y, mode)
         assert got.size == want.size and np.array_equal(got, want), (x, y, MODE_NAMES[mode])
         del out, keys, got, want
-    ctx.set_stream(0)
+    unbind_stream(ctx)
 
 
 def test_config4_full_size(ctx, oracle):

@@ -18,7 +18,7 @@ import numpy as np
 import pytest
 
 from rtc_b200 import scenes
-from rtc_b200._types import FLAG_NORMALS_SATURATE, RGB_ASCII, RGB_NORMALS, RGB_PIXEL, BIT_PIXEL, mode_bpp, mode_has_glyph
+from rtc_b200._types import FLAG_NORMALS_SATURATE, FLAG_UPDATE_REF_LAUNCH_LIMIT, RGB_ASCII, RGB_NORMALS, RGB_PIXEL, BIT_PIXEL, mode_bpp, mode_has_glyph
 from util import PI32
 
 pytestmark = pytest.mark.gpu
@@ -60,7 +60,11 @@ def compare(ctx, name, exe_name, objs, p, mode, tmp_path, flags=0):
     miss_b = (b == (16 if bpp == 1 else 0)).all(axis=1)
     st = {"pixels": int(n_px), "identical": int((d == 0).sum()), "within_1": int((d <= 1).sum()), "max_diff": int(d.max(initial=0)),
           "off_by_more_than_1": int((d > 1).sum()), "hit_mask_flips": int((miss_a != miss_b).sum()),
-          "ref_stream_bytes": info.get("stream_bytes"), "ours_stream_bytes": int(len(ctx.frame_ansi()))}
+          "stream_bytes": int(len(ctx.frame_ansi()))}
+    # the reference's RayTracingManager::Update runs its physics step first (for <= 1024 objects): compare stream lengths like for like
+    ctx.set_objects(objs)
+    st["stream_bytes_after_update"] = int(len(ctx.update(p, mode, dt=0.0, flags=flags | FLAG_UPDATE_REF_LAUNCH_LIMIT)))
+    st["ref_stream_bytes_after_update"] = info.get("stream_bytes")
     if mode_has_glyph(mode):
         st["glyph_differs"] = int((glyph != ref_glyph).sum())
     STATS["%s/%s" % (name, exe_name)] = st

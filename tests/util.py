@@ -57,3 +57,21 @@ def parse_stream(stream, x, y, mode):
             i += 1
     assert i == len(s), "trailing bytes in stream"
     return keys.reshape(-1), glyphs, full
+
+
+def bind_stream(ctx):
+    """Run torch and the rtc context on ONE explicit stream.  (rtc_set_stream(NULL) means "the context's own non-blocking
+    stream", never the legacy default stream -- handing it torch's default stream would leave the rtc kernels unordered
+    against the torch kernels that produce their inputs.)"""
+    import torch
+    s = torch.cuda.Stream()
+    torch.cuda.set_stream(s)
+    ctx.set_stream(s.cuda_stream)
+    return s
+
+
+def unbind_stream(ctx):
+    import torch
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(torch.cuda.default_stream())
+    ctx.set_stream(0)
