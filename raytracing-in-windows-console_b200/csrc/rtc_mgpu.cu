@@ -112,6 +112,12 @@ struct FrameSlot {                                   // shared between the worke
     bool host_registered = false;                    // mmap + cudaHostRegister (NUMA placement) instead of cudaHostAlloc
 };
 
+struct InFlight {
+    long long frame = 0;
+    int stage = 0;                                   // 0 kernels running, 1 length published, 2 copy issued
+    std::chrono::steady_clock::time_point t_done, t_issue;
+};
+
 struct Worker {
     int g = 0, device = 0;
     rtc_ctx* ctx = nullptr;
@@ -119,8 +125,7 @@ struct Worker {
     std::mutex mu;
     std::condition_variable cv;
     std::deque<Cmd> q;
-    std::deque<long long> inflight;                  // frames enqueued on the device, oldest first
-    int stage = 0;                                   // progress of inflight.front(): 0 kernels running, 1 length published, 2 copy issued
+    std::deque<InFlight> inflight;                   // frames enqueued on the device, oldest first
     rtc::DevBuf<uint8_t> d_color, d_glyph;           // HOST gather: this device's band planes (+1 context row)
     rtc::DevBuf<char> d_out[kSlots];
     unsigned long long* h_total = nullptr;           // [kSlots], mapped pinned: the emit kernel writes the length here
@@ -132,7 +137,6 @@ struct Worker {
     // (waiting for the lengths of the devices before this one), and from "copy issued" to "copy landed"
     double us_enqueue = 0.0, us_wait_len = 0.0, us_copy = 0.0;
     unsigned long long n_frames = 0;
-    std::chrono::steady_clock::time_point t_done, t_issue;
 };
 
 }  // namespace
@@ -332,70 +336,90 @@ int enqueue_frame(rtc_mgpu* m, Worker& w, const Cmd& cmd)
     return RTC_OK;
 }
 
-// One non-blocking step of the oldest in-flight frame of this worker; true if something moved.
+// One non-blocking pass over this worker's in-flight frames; true if something moved.  Every frame walks through
+//   0 kernels running -> 1 length published -> 2 copy issued -> landed (popped)
+// on its own: the length of frame k+1 is published the moment its kernels finish, even while the copy of frame k is
+// still on the wire (the devices behind this one need that length to place THEIR pieces of frame k+1 -- holding it back
+// until the older copy has landed cost them > 100 us per frame).  Copies are issued in frame order.
 bool progress(rtc_mgpu* m, Worker& w)
 {
     if (w.inflight.empty()) return false;
-    const long long j = w.inflight.front();
-    const int slot = (int)(j % kSlots), g = w.g;
-    FrameSlot& f = m->fr[slot];
+    const int g = w.g;
     const bool owns_stream = m->gather == RTC_GATHER_HOST || g == 0;     // has a piece of the stream to land
-    auto finish = [&](int rc) {
-        f.rc[g] = rc;
-        if (rc) {
-            f.len[g] = 0;
-            set_error(m, g, rc, rtc_last_error());
+    bool moved = false;
+    bool older_copies_issued = true;
+    for (size_t i = 0; i < w.inflight.size();) {
+        InFlight& e = w.inflight[i];
+        const long long j = e.frame;
+        const int slot = (int)(j % kSlots);
+        FrameSlot& f = m->fr[slot];
+        auto finish = [&](int rc) {                              // only ever reached for the oldest frame (stream order)
+            f.rc[g] = rc;
+            if (rc) {
+                f.len[g] = 0;
+                set_error(m, g, rc, rtc_last_error());
+                f.len_tag[g].store(j + 1, std::memory_order_release);
+            }
+            f.done_tag[g].store(j + 1, std::memory_order_release);
+            w.inflight.erase(w.inflight.begin() + (long)i);
+            moved = true;
+        };
+        if (m->failed.load(std::memory_order_relaxed)) { finish(f.rc[g] ? f.rc[g] : RTC_ERR_CUDA); continue; }
+        if (e.stage == 0) {
+            const cudaError_t q = cudaEventQuery(w.ev_t1[slot]);
+            if (q == cudaErrorNotReady) break;                   // the frames behind it run on the same stream: not ready either
+            if (q != cudaSuccess) { fail(RTC_ERR_CUDA, "frame %lld failed on the device: %s", j, cudaGetErrorString(q)); finish(RTC_ERR_CUDA); continue; }
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, w.ev_t0[slot], w.ev_t1[slot]);
+            f.ms[g] = ms;
+            if (m->gather == RTC_GATHER_P2P && g == 0) {
+                float enc = 0.f;
+                cudaEventElapsedTime(&enc, w.ev_mid[slot], w.ev_t1[slot]);
+                f.enc_ms = enc;
+            }
+            f.len[g] = owns_stream ? w.h_total[slot] : 0ull;
             f.len_tag[g].store(j + 1, std::memory_order_release);
+            e.stage = 1;
+            e.t_done = std::chrono::steady_clock::now();
+            moved = true;
+            if (!owns_stream) { finish(RTC_OK); continue; }
         }
-        f.done_tag[g].store(j + 1, std::memory_order_release);
-        w.inflight.pop_front();
-        w.stage = 0;
-    };
-    if (m->failed.load(std::memory_order_relaxed)) { finish(f.rc[g] ? f.rc[g] : RTC_ERR_CUDA); return true; }
-    if (w.stage == 0) {
-        const cudaError_t q = cudaEventQuery(w.ev_t1[slot]);
-        if (q == cudaErrorNotReady) return false;
-        if (q != cudaSuccess) { fail(RTC_ERR_CUDA, "frame %lld failed on the device: %s", j, cudaGetErrorString(q)); finish(RTC_ERR_CUDA); return true; }
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, w.ev_t0[slot], w.ev_t1[slot]);
-        f.ms[g] = ms;
-        if (m->gather == RTC_GATHER_P2P && g == 0) {
-            float e = 0.f;
-            cudaEventElapsedTime(&e, w.ev_mid[slot], w.ev_t1[slot]);
-            f.enc_ms = e;
-        }
-        f.len[g] = owns_stream ? w.h_total[slot] : 0ull;
-        f.len_tag[g].store(j + 1, std::memory_order_release);
-        w.stage = 1;
-        w.t_done = std::chrono::steady_clock::now();
-        if (!owns_stream) { finish(RTC_OK); return true; }
-    }
-    if (w.stage == 1) {
-        unsigned long long off = 0;
-        if (m->gather == RTC_GATHER_HOST) {
-            for (int h = 0; h < g; ++h) {
-                if (f.len_tag[h].load(std::memory_order_acquire) < j + 1) return false;    // lengths before me are not all known yet
-                off += f.len[h];
+        if (e.stage == 1) {
+            bool ready = older_copies_issued;
+            unsigned long long off = 0;
+            if (ready && m->gather == RTC_GATHER_HOST) {
+                for (int h = 0; h < g; ++h) {
+                    if (f.len_tag[h].load(std::memory_order_acquire) < j + 1) { ready = false; break; }    // a length before mine is not known yet
+                    off += f.len[h];
+                }
+            }
+            if (ready) {
+                const unsigned long long nbytes = f.len[g];
+                if (off + nbytes > f.host_cap) { fail(RTC_ERR_CAPACITY, "stream piece [%llu, +%llu) exceeds the frame buffer (%zu B)", off, nbytes, f.host_cap); finish(RTC_ERR_CAPACITY); continue; }
+                cudaError_t ce = cudaSuccess;
+                if (nbytes) ce = cudaMemcpyAsync(f.host + off, w.d_out[slot].p, nbytes, cudaMemcpyDeviceToHost, w.copy_stream);
+                if (ce == cudaSuccess) ce = cudaEventRecord(w.ev_copy[slot], w.copy_stream);
+                if (ce != cudaSuccess) { fail(RTC_ERR_CUDA, "D2H of the band stream failed: %s", cudaGetErrorString(ce)); finish(RTC_ERR_CUDA); continue; }
+                e.stage = 2;
+                e.t_issue = std::chrono::steady_clock::now();
+                w.us_wait_len += std::chrono::duration<double, std::micro>(e.t_issue - e.t_done).count();
+                moved = true;
+            } else {
+                older_copies_issued = false;
             }
         }
-        const unsigned long long nbytes = f.len[g];
-        if (off + nbytes > f.host_cap) { fail(RTC_ERR_CAPACITY, "stream piece [%llu, +%llu) exceeds the frame buffer (%zu B)", off, nbytes, f.host_cap); finish(RTC_ERR_CAPACITY); return true; }
-        cudaError_t e = cudaSuccess;
-        if (nbytes) e = cudaMemcpyAsync(f.host + off, w.d_out[slot].p, nbytes, cudaMemcpyDeviceToHost, w.copy_stream);
-        if (e == cudaSuccess) e = cudaEventRecord(w.ev_copy[slot], w.copy_stream);
-        if (e != cudaSuccess) { fail(RTC_ERR_CUDA, "D2H of the band stream failed: %s", cudaGetErrorString(e)); finish(RTC_ERR_CUDA); return true; }
-        w.stage = 2;
-        w.t_issue = std::chrono::steady_clock::now();
-        w.us_wait_len += std::chrono::duration<double, std::micro>(w.t_issue - w.t_done).count();
+        if (e.stage == 2 && i == 0) {
+            const cudaError_t q = cudaEventQuery(w.ev_copy[slot]);
+            if (q != cudaErrorNotReady) {
+                if (q != cudaSuccess) { fail(RTC_ERR_CUDA, "D2H of the band stream failed: %s", cudaGetErrorString(q)); finish(RTC_ERR_CUDA); continue; }
+                w.us_copy += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - e.t_issue).count();
+                finish(RTC_OK);
+                continue;
+            }
+        }
+        ++i;
     }
-    if (w.stage == 2) {
-        const cudaError_t q = cudaEventQuery(w.ev_copy[slot]);
-        if (q == cudaErrorNotReady) return false;
-        if (q != cudaSuccess) { fail(RTC_ERR_CUDA, "D2H of the band stream failed: %s", cudaGetErrorString(q)); finish(RTC_ERR_CUDA); return true; }
-        w.us_copy += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - w.t_issue).count();
-        finish(RTC_OK);
-    }
-    return true;
+    return moved;
 }
 
 void worker_main(rtc_mgpu* m, Worker* w)
@@ -425,7 +449,9 @@ void worker_main(rtc_mgpu* m, Worker* w)
                 f.len_tag[w->g].store(cmd.frame + 1, std::memory_order_release);
                 f.done_tag[w->g].store(cmd.frame + 1, std::memory_order_release);
             } else {
-                w->inflight.push_back(cmd.frame);
+                InFlight fl;
+                fl.frame = cmd.frame;
+                w->inflight.push_back(fl);
             }
         }
         const bool moved = progress(m, *w);
