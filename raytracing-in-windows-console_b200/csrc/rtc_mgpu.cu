@@ -366,6 +366,8 @@ bool progress(rtc_mgpu* m, Worker& w)
         };
         if (m->failed.load(std::memory_order_relaxed)) { finish(f.rc[g] ? f.rc[g] : RTC_ERR_CUDA); continue; }
         if (e.stage == 0) {
+            static const bool serial = getenv("RTC_MGPU_SERIAL_STAGES") != nullptr;   // experiment: the first version's behaviour
+            if (serial && i != 0) break;
             const cudaError_t q = cudaEventQuery(w.ev_t1[slot]);
             if (q == cudaErrorNotReady) break;                   // the frames behind it run on the same stream: not ready either
             if (q != cudaSuccess) { fail(RTC_ERR_CUDA, "frame %lld failed on the device: %s", j, cudaGetErrorString(q)); finish(RTC_ERR_CUDA); continue; }
