@@ -304,6 +304,8 @@ RTC_API int rtc_mgpu_last_frame(rtc_mgpu* m, float* device_ms, uint32_t* rows, f
  * per frame spent enqueueing (scene staging + launches), waiting for the stream lengths of the devices before it, and in
  * its D2H copy.                                                                                                       */
 RTC_API int rtc_mgpu_host_stats(rtc_mgpu* m, float* out);
+/* Debug: host-clock timeline of the last 64 frames (layout in rtc_mgpu.cu); out holds (n_gpus * 6 + 2) * 64 doubles.    */
+RTC_API int rtc_mgpu_debug_trace(rtc_mgpu* m, double* out);
 /* Explicit band boundaries rows[0..n_gpus] for frames of height y (NULL: automatic -- equal bands; in the P2P gather
  * device 0's band shrinks by the measured cost of the encoder).                                                       */
 RTC_API int rtc_mgpu_set_bands(rtc_mgpu* m, uint32_t y, const uint32_t* rows);

@@ -28,7 +28,7 @@ EXPORTS = [
     "rtc_mgpu_create", "rtc_mgpu_destroy", "rtc_mgpu_count", "rtc_mgpu_context", "rtc_mgpu_scene_clear",
     "rtc_mgpu_scene_add_sphere", "rtc_mgpu_scene_add_plane", "rtc_mgpu_scene_set_objects", "rtc_mgpu_scene_get_objects",
     "rtc_mgpu_set_light", "rtc_mgpu_submit", "rtc_mgpu_collect", "rtc_mgpu_update", "rtc_mgpu_last_frame",
-    "rtc_mgpu_set_bands", "rtc_mgpu_flush_l2", "rtc_mgpu_host_stats", "rtc_plan_bands",
+    "rtc_mgpu_set_bands", "rtc_mgpu_flush_l2", "rtc_mgpu_host_stats", "rtc_mgpu_debug_trace", "rtc_plan_bands",
 ]
 
 GATHER_HOST, GATHER_P2P = 0, 1
@@ -111,6 +111,7 @@ def load_library(build_if_missing=True):
     L.rtc_mgpu_set_bands.argtypes = [vp, u32, vp]
     L.rtc_mgpu_flush_l2.argtypes = [vp]
     L.rtc_mgpu_host_stats.argtypes = [vp, vp]
+    L.rtc_mgpu_debug_trace.argtypes = [vp, vp]
     L.rtc_plan_bands.argtypes = [u32, i32, u32, f64, u32, vp]
     _lib = L
     return L
@@ -241,6 +242,12 @@ class MultiGpu:
 
     def flush_l2(self):
         _check(self.L.rtc_mgpu_flush_l2(self._h))
+
+    def debug_trace(self):
+        """(workers[n][64][6], main[64][2]) host-clock timeline of the last 64 frames, in us."""
+        a = np.zeros((self.n * 6 + 2) * 64, np.float64)
+        _check(self.L.rtc_mgpu_debug_trace(self._h, a.ctypes.data))
+        return a[:self.n * 64 * 6].reshape(self.n, 64, 6), a[self.n * 64 * 6:].reshape(64, 2)
 
     def host_stats(self):
         """Per device, average us per frame since the last call: enqueue, wait for lengths, D2H copy."""

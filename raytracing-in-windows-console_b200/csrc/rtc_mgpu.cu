@@ -137,11 +137,14 @@ struct Worker {
     // (waiting for the lengths of the devices before this one), and from "copy issued" to "copy landed"
     double us_enqueue = 0.0, us_wait_len = 0.0, us_copy = 0.0;
     unsigned long long n_frames = 0;
+    double trace[64][6] = {};                        // rtc_mgpu_debug_trace: per frame % 64, host-clock us since the driver's epoch
 };
 
 }  // namespace
 
 struct rtc_mgpu {
+    std::chrono::steady_clock::time_point epoch = std::chrono::steady_clock::now();
+    double main_trace[64][2] = {};                   // submit called, collect returned
     int n = 0;
     int gather = RTC_GATHER_HOST;
     Worker w[kMaxGpus];
@@ -169,6 +172,11 @@ struct rtc_mgpu {
 };
 
 namespace {
+
+inline double us_since(const rtc_mgpu* m)
+{
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - m->epoch).count();
+}
 
 void set_error(rtc_mgpu* m, int g, int code, const char* what)
 {
@@ -383,6 +391,8 @@ bool progress(rtc_mgpu* m, Worker& w)
             f.len_tag[g].store(j + 1, std::memory_order_release);
             e.stage = 1;
             e.t_done = std::chrono::steady_clock::now();
+            w.trace[j & 63][2] = us_since(m);
+            w.trace[j & 63][5] = ms * 1000.0;
             moved = true;
             if (!owns_stream) { finish(RTC_OK); continue; }
         }
@@ -404,6 +414,7 @@ bool progress(rtc_mgpu* m, Worker& w)
                 if (ce != cudaSuccess) { fail(RTC_ERR_CUDA, "D2H of the band stream failed: %s", cudaGetErrorString(ce)); finish(RTC_ERR_CUDA); continue; }
                 e.stage = 2;
                 e.t_issue = std::chrono::steady_clock::now();
+                w.trace[j & 63][3] = us_since(m);
                 w.us_wait_len += std::chrono::duration<double, std::micro>(e.t_issue - e.t_done).count();
                 moved = true;
             } else {
@@ -415,6 +426,7 @@ bool progress(rtc_mgpu* m, Worker& w)
             if (q != cudaErrorNotReady) {
                 if (q != cudaSuccess) { fail(RTC_ERR_CUDA, "D2H of the band stream failed: %s", cudaGetErrorString(q)); finish(RTC_ERR_CUDA); continue; }
                 w.us_copy += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - e.t_issue).count();
+                w.trace[j & 63][4] = us_since(m);
                 finish(RTC_OK);
                 continue;
             }
@@ -439,7 +451,9 @@ void worker_main(rtc_mgpu* m, Worker* w)
             if (cmd.type == Cmd::QUIT) break;
             const int slot = (int)(cmd.frame % kSlots);
             const auto tq0 = std::chrono::steady_clock::now();
+            w->trace[cmd.frame & 63][0] = us_since(m);
             int rc = m->failed.load() ? RTC_ERR_CUDA : enqueue_frame(m, *w, cmd);
+            w->trace[cmd.frame & 63][1] = us_since(m);
             w->us_enqueue += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tq0).count();
             w->n_frames++;
             if (rc) {                                            // publish the failure so that nobody waits for this band
@@ -784,6 +798,7 @@ int rtc_mgpu_submit(rtc_mgpu* m, const rtc_params* p, rtc_mode mode, double dt, 
         { std::lock_guard<std::mutex> lk(w.mu); w.q.push_back(cmd); }
         w.cv.notify_one();
     }
+    m->main_trace[j & 63][0] = us_since(m);
     m->n_sub = j + 1;
     return RTC_OK;
 }
@@ -814,6 +829,7 @@ int rtc_mgpu_collect(rtc_mgpu* m, const char** host_ptr, size_t* n_bytes)
     memcpy(m->last_rows, f.rows, sizeof(uint32_t) * (m->n + 1));
     *host_ptr = f.host;
     *n_bytes = total;
+    m->main_trace[j & 63][1] = us_since(m);
     return RTC_OK;
 }
 
@@ -839,6 +855,18 @@ int rtc_mgpu_host_stats(rtc_mgpu* m, float* out)
         out[3 * g + 0] = (float)(w.us_enqueue / n); out[3 * g + 1] = (float)(w.us_wait_len / n); out[3 * g + 2] = (float)(w.us_copy / n);
         w.us_enqueue = w.us_wait_len = w.us_copy = 0.0; w.n_frames = 0;
     }
+    return RTC_OK;
+}
+
+// Debug: host-clock timeline (us since creation) of the last 64 frames.  out[(g * 64 + k) * 6 + i], k = frame % 64:
+// i = 0 enqueue start, 1 enqueue end, 2 kernels seen finished, 3 copy issued, 4 copy landed, 5 device time of the frame
+// (us); then out[n * 64 * 6 + k * 2 + {0, 1}] = rtc_mgpu_submit called / rtc_mgpu_collect returned.  Idle pipeline only.
+int rtc_mgpu_debug_trace(rtc_mgpu* m, double* out)
+{
+    if (!m || !out) return fail(RTC_ERR_INVALID, "NULL argument");
+    if (m->n_sub != m->n_col) return fail(RTC_ERR_INVALID, "frames are in flight: collect them first");
+    for (int g = 0; g < m->n; ++g) memcpy(out + (size_t)g * 64 * 6, m->w[g].trace, sizeof(double) * 64 * 6);
+    memcpy(out + (size_t)m->n * 64 * 6, m->main_trace, sizeof(double) * 64 * 2);
     return RTC_OK;
 }
 
