@@ -83,7 +83,7 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
 
     def __init__(self, index):
-        self.index = index
+        self.index = index if isinstance(index, (list, tuple)) else [index]      # one GPU or several (median / max over all)
         self.samples = []
         self.reasons = set()
         self.max_mhz = None
@@ -96,13 +96,15 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0]))
-                self.max_mhz = float(out[1])
-                for nm, v in zip(names, out[2:6]):
-                    if v.strip().lower().startswith("active"):
-                        self.reasons.add(nm)
+                txt = subprocess.run(["nvidia-smi", "-i", ",".join(str(i) for i in self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                for ln in txt.splitlines():
+                    out = ln.split(",")
+                    self.samples.append(float(out[0]))
+                    self.max_mhz = float(out[1])
+                    for nm, v in zip(names, out[2:6]):
+                        if v.strip().lower().startswith("active"):
+                            self.reasons.add(nm)
             except Exception:
                 pass
             self._stop.wait(0.1)
@@ -116,7 +118,8 @@ class ClockSampler:
         if self._th:
             self._th.join(timeout=6)
         med = float(np.median(self.samples)) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "sm_mhz_min": float(np.min(self.samples)) if self.samples else None}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -265,7 +268,7 @@ def sha16(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
 
 
-def measure_ctx(ctx, torch, stream, flush, objs, cams, mode, flags, steps, warmup, e2e_steps=None):
+def measure_ctx(ctx, torch, stream, flush, objs, cams, mode, flags, steps, warmup, e2e_steps=None, sample_e2e_clocks=False):
     """One GPU through rtc_ctx.  Device-timed frames (CUDA events on the launching stream, L2 flushed between steps)
     and the end-to-end loop through rtc_scene_set_objects + rtc_submit / rtc_collect with host buffers."""
     import rtc_b200
@@ -305,6 +308,10 @@ def measure_ctx(ctx, torch, stream, flush, objs, cams, mode, flags, steps, warmu
     torch.cuda.synchronize()
     ctx.set_objects(objs)
     ctx.submit(cam(), mode, 0.0, upd)
+    sampler = ClockSampler(ctx.device) if sample_e2e_clocks else None
+    if sampler:                                    # (the pipelined loop keeps the GPU busy back to back: sustained, not boost, clocks)
+        sampler.start()
+        n = max(n, int(1500.0 / max(res["ms_per_step"], 1e-3)))      # >= 1.5 s so that nvidia-smi gets a few samples in
     t0 = time.perf_counter()
     nbytes = 0
     for _ in range(n):
@@ -313,6 +320,8 @@ def measure_ctx(ctx, torch, stream, flush, objs, cams, mode, flags, steps, warmu
         nbytes = len(ctx.collect())                # frame k: stream in pinned host memory
     t1 = time.perf_counter()
     ctx.collect()
+    if sampler:
+        res["e2e_clocks"] = sampler.stop()
     res["e2e_ms"] = (t1 - t0) * 1e3 / n
     res["d2h_bytes"] = int(nbytes + 8)
     res["h2d_bytes"] = int(objs.nbytes + 96)
@@ -324,7 +333,7 @@ def measure_ctx(ctx, torch, stream, flush, objs, cams, mode, flags, steps, warmu
     return res
 
 
-def measure_mgpu(m, objs, cams, mode, flags, steps, warmup, e2e_steps=None):
+def measure_mgpu(m, objs, cams, mode, flags, steps, warmup, e2e_steps=None, sample_e2e_clocks=False):
     """N GPUs through rtc_mgpu (one process, row bands).  `value`: per step every device's L2 is flushed (untimed), the
     frame is submitted and collected; the step's time is what the CUDA events on each device's stream say (first kernel
     to end of that device's last kernel; in the p2p gather device 0's last kernel is the encode of the assembled frame);
@@ -354,6 +363,10 @@ def measure_mgpu(m, objs, cams, mode, flags, steps, warmup, e2e_steps=None):
            "encode_ms_on_gpu0": enc / steps}
     n = e2e_steps or steps
     m.host_stats()                                 # reset the driver's host-side accounting
+    sampler = ClockSampler(sorted(set(m.devices))) if sample_e2e_clocks else None
+    if sampler:                                    # (the pipelined loop keeps every GPU busy back to back: sustained, not boost, clocks)
+        sampler.start()
+        n = max(n, int(1500.0 / max(res["ms_per_step"], 1e-3)))      # >= 1.5 s so that nvidia-smi gets a few samples in
     m.set_objects(objs)
     m.submit(cam(), mode, 0.0, upd)
     m.set_objects(objs)
@@ -366,7 +379,11 @@ def measure_mgpu(m, objs, cams, mode, flags, steps, warmup, e2e_steps=None):
         nbytes = len(m.collect())                  # frame k: the assembled stream in pinned host memory
     t1 = time.perf_counter()
     m.collect(); m.collect()
+    if sampler:
+        res["e2e_clocks"] = sampler.stop()
     res["host_us_per_frame"] = m.host_stats()
+    w, _ = m.debug_trace()
+    res["device_us_in_pipelined_loop"] = [round(float(np.median(w[g][:, 5])), 1) for g in range(m.n)]
     res["e2e_ms"] = (t1 - t0) * 1e3 / n
     res["d2h_bytes"] = int(nbytes + 8 * m.n)
     res["h2d_bytes"] = int(objs.nbytes + 96) * m.n
@@ -446,11 +463,11 @@ def run_ours(args):
     sampler.start()
     m = None
     if N == 1:
-        r = measure_ctx(ctx, torch, stream, flush, objs, cams, mode, rflags, args.steps, args.warmup)
+        r = measure_ctx(ctx, torch, stream, flush, objs, cams, mode, rflags, args.steps, args.warmup, sample_e2e_clocks=True)
     else:
         gather = rtc_b200.GATHER_P2P if args.gather == "p2p" else rtc_b200.GATHER_HOST
         m = rtc_b200.MultiGpu(devices, gather)
-        r = measure_mgpu(m, objs, cams, mode, rflags, args.steps, args.warmup)
+        r = measure_mgpu(m, objs, cams, mode, rflags, args.steps, args.warmup, sample_e2e_clocks=True)
     clocks = sampler.stop()
     ms_per_step = r["ms_per_step"]
     if dist is not None:
@@ -473,6 +490,9 @@ def run_ours(args):
            "synchronous_update": {"value": mr(r["sync_ms"]), "ms_per_step": r["sync_ms"]}}
     if "host_us_per_frame" in r:
         e2e["worker_threads_us_per_frame"] = r["host_us_per_frame"]
+        e2e["device_us_per_frame_in_this_loop"] = r["device_us_in_pipelined_loop"]
+    if "e2e_clocks" in r:
+        e2e["clocks"] = r["e2e_clocks"]
 
     pk = peaks()
     sm_count = ctx.device_info()["sm_count"]
@@ -535,6 +555,22 @@ def run_ours(args):
                                              "cells_per_ns": frame_rays / (enc_ms * 1e6)}
         line["stages_ms"] = r["stages_ms"]
         line["gpu_launches"] = int(r["launches_per_step"] * args.steps)
+        # What the shade + quantise epilogue costs inside the ray kernel: the same frames in SDL mode, which traces and
+        # writes nothing (reference RayTracing.cu:755-795) -- same kernel, epilogue off.
+        try:
+            ctx.set_objects(objs)
+            t_sdl = 0.0
+            for i in range(13):
+                flush.zero_()
+                ctx.render(cams[i % len(cams)], rtc_b200.SDL, rflags)
+                torch.cuda.synchronize()
+                if i >= 3:
+                    t_sdl += ctx.timings()["trace_ms"]
+            t_sdl /= 10
+            line["shade_epilogue"] = {"trace_ms_with_epilogue": trace_ms, "trace_ms_sdl_mode_no_epilogue": t_sdl, "epilogue_ms": trace_ms - t_sdl,
+                                      "roofline_frac_of_the_bare_trace": 7.0 * frame_rays * n_spheres * n_passes / (t_sdl * 1e-3) / 1e12 / fp32_peak}
+        except Exception as e:
+            line["shade_epilogue"] = {"error": repr(e)}
     else:
         line["per_device_ms"] = r["per_device_ms"]
         line["encode_ms_on_gpu0"] = r["encode_ms_on_gpu0"]
