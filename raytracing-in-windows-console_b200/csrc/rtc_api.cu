@@ -544,11 +544,10 @@ int rtc_render(rtc_ctx* c, const rtc_params* p, rtc_mode mode, uint32_t flags)
     int rc = trace_shade(c, p, mode, flags, 0, p->y, c->d_color.p, mode_has_glyph(mode) ? c->d_glyph.p : nullptr, true);
     if (rc) return rc;
     rc = do_encode(c, c->d_color.p, mode_has_glyph(mode) ? c->d_glyph.p : nullptr, p->x, p->y, mode, c->d_out[slot].p, cap,
-                   c->d_total.p + slot, false);
+                   c->h_total.p + slot, false);        // the emit kernel writes the stream length straight into pinned host memory
     if (rc) return rc;
-    c->last_launches += 2;
+    c->last_launches += (mode == RTC_SDL || p->x <= 1u) ? 1u : 2u;   // newline kernel, or count + emit
     CK(cudaEventRecord(c->ev[4], c->stream));
-    CK(cudaMemcpyAsync(c->h_total.p + slot, c->d_total.p + slot, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaEventRecord(c->ev_total[slot], c->stream));
     c->cur = slot;
     c->slot_cap[slot] = cap;
