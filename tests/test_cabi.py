@@ -50,6 +50,8 @@ def test_no_cpu_fallback(rtc):
         pytest.skip("a GPU is present")
     with pytest.raises(rtc.RtcError, match="no usable CUDA device|CUDA"):
         rtc.Context(0)
+    with pytest.raises(rtc.RtcError, match="no usable CUDA device|CUDA"):
+        rtc.MultiGpu([0, 0])                              # the multi-GPU frame driver has no CPU fallback either
 
 
 def test_product_does_not_import_oracle():

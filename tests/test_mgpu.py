@@ -59,6 +59,10 @@ def test_mgpu_pipelined_frames_equal_single_gpu(ctx, rtc, gather, devices):
             assert np.array_equal(got[k], want[k]), f"frame {k} ({MODE_NAMES[modes[k]]}) differs on {len(devices)} bands, gather {gather}"
         info = m.last_frame()
         assert info["bands"][0][0] == 0 and info["bands"][-1][1] == y and len(info["device_ms"]) == len(devices)
+        st = m.host_stats()                                          # host-side accounting of the driver's worker threads
+        assert len(st["enqueue_us"]) == len(devices) and all(v > 0 for v in st["enqueue_us"])
+        workers, main = m.debug_trace()
+        assert workers.shape == (len(devices), 64, 6) and main.shape == (64, 2)
         # the replicas ran the same physics
         ctx.set_objects(objs)
         for _ in range(len(ps)):
