@@ -328,12 +328,12 @@ int enqueue_frame(rtc_mgpu* m, Worker& w, const Cmd& cmd)
         CK(cudaEventRecord(w.ev_t1[slot], c->stream));
         return RTC_OK;
     }
-    CK(cudaEventRecord(w.ev_mid[slot], c->stream));
     for (int h = 1; h < n; ++h) {
         if (!wait_for(m, [&] { return m->enq_tag[h].load(std::memory_order_acquire) >= cmd.frame + 1; }))
             return fail(RTC_ERR_CUDA, "timed out waiting for device slot %d to enqueue its band", h);
         CK(cudaStreamWaitEvent(c->stream, m->w[h].ev_band[ps], 0));
     }
+    CK(cudaEventRecord(w.ev_mid[slot], c->stream));            // every band has landed: what follows is the encode alone
     const size_t cap = rtc_encode_capacity(x, f.y, (rtc_mode)mode);
     CK(w.d_out[slot].ensure(cap));
     rc = rtc::do_encode(c, m->plane_color[ps].p, gl ? m->plane_glyph[ps].p : nullptr, x, f.y, mode, w.d_out[slot].p, cap, w.h_total + slot, false);
