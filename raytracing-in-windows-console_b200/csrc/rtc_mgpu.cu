@@ -102,7 +102,8 @@ struct FrameSlot {                                   // shared between the worke
     std::atomic<long long> done_tag[kMaxGpus];       // frame id + 1 whose piece device g has landed in `host`
     unsigned long long len[kMaxGpus];
     float ms[kMaxGpus];                              // device time of the frame's kernels on device g (CUDA events)
-    float enc_ms;                                    // P2P: encode time on device 0
+    float enc_ms;                                    // P2P: encode time on device 0 ...
+    float own_ms;                                    // ... and the time of its own band
     int rc[kMaxGpus];
     uint32_t rows[kMaxGpus + 1];
     uint32_t x = 0, y = 0;
@@ -129,7 +130,7 @@ struct Worker {
     rtc::DevBuf<uint8_t> d_color, d_glyph;           // HOST gather: this device's band planes (+1 context row)
     rtc::DevBuf<char> d_out[kSlots];
     unsigned long long* h_total = nullptr;           // [kSlots], mapped pinned: the emit kernel writes the length here
-    cudaEvent_t ev_t0[kSlots] = {}, ev_t1[kSlots] = {}, ev_mid[kSlots] = {}, ev_copy[kSlots] = {};
+    cudaEvent_t ev_t0[kSlots] = {}, ev_t1[kSlots] = {}, ev_own[kSlots] = {}, ev_mid[kSlots] = {}, ev_copy[kSlots] = {};
     cudaEvent_t ev_band[kPlaneSlots] = {};           // P2P: this device's band of the frame in plane slot s has been written
     cudaStream_t copy_stream = nullptr;
     rtc::DevBuf<unsigned char> d_flush;
@@ -167,7 +168,7 @@ struct rtc_mgpu {
     std::string err;
     int err_code = 0;
     float last_ms[kMaxGpus] = {};
-    float last_enc_ms = 0.f;
+    float last_enc_ms = 0.f, last_own_ms = 0.f;
     uint32_t last_rows[kMaxGpus + 1] = {};
 };
 
@@ -328,6 +329,7 @@ int enqueue_frame(rtc_mgpu* m, Worker& w, const Cmd& cmd)
         CK(cudaEventRecord(w.ev_t1[slot], c->stream));
         return RTC_OK;
     }
+    CK(cudaEventRecord(w.ev_own[slot], c->stream));            // device 0's own band is done
     for (int h = 1; h < n; ++h) {
         if (!wait_for(m, [&] { return m->enq_tag[h].load(std::memory_order_acquire) >= cmd.frame + 1; }))
             return fail(RTC_ERR_CUDA, "timed out waiting for device slot %d to enqueue its band", h);
@@ -383,9 +385,11 @@ bool progress(rtc_mgpu* m, Worker& w)
             cudaEventElapsedTime(&ms, w.ev_t0[slot], w.ev_t1[slot]);
             f.ms[g] = ms;
             if (m->gather == RTC_GATHER_P2P && g == 0) {
-                float enc = 0.f;
+                float enc = 0.f, own = 0.f;
                 cudaEventElapsedTime(&enc, w.ev_mid[slot], w.ev_t1[slot]);
+                cudaEventElapsedTime(&own, w.ev_t0[slot], w.ev_own[slot]);
                 f.enc_ms = enc;
+                f.own_ms = own;
             }
             f.len[g] = owns_stream ? w.h_total[slot] : 0ull;
             f.len_tag[g].store(j + 1, std::memory_order_release);
@@ -568,6 +572,7 @@ int rtc_mgpu_create(rtc_mgpu** out, int n_gpus, const int* device_ids, int gathe
             CKM(cudaEventCreate(&w.ev_t0[s]));
             CKM(cudaEventCreate(&w.ev_t1[s]));
             CKM(cudaEventCreate(&w.ev_mid[s]));
+            CKM(cudaEventCreate(&w.ev_own[s]));
             CKM(cudaEventCreateWithFlags(&w.ev_copy[s], cudaEventDisableTiming));
         }
         for (int s = 0; s < kPlaneSlots; ++s) CKM(cudaEventCreateWithFlags(&w.ev_band[s], cudaEventDisableTiming));
@@ -621,6 +626,7 @@ void rtc_mgpu_destroy(rtc_mgpu* m)
             if (w.ev_t0[s]) cudaEventDestroy(w.ev_t0[s]);
             if (w.ev_t1[s]) cudaEventDestroy(w.ev_t1[s]);
             if (w.ev_mid[s]) cudaEventDestroy(w.ev_mid[s]);
+            if (w.ev_own[s]) cudaEventDestroy(w.ev_own[s]);
             if (w.ev_copy[s]) cudaEventDestroy(w.ev_copy[s]);
         }
         for (int s = 0; s < kPlaneSlots; ++s) if (w.ev_band[s]) cudaEventDestroy(w.ev_band[s]);
@@ -765,7 +771,7 @@ int rtc_mgpu_submit(rtc_mgpu* m, const rtc_params* p, rtc_mode mode, double dt, 
     // P2P: once a few frames have been timed, give device 0 a smaller band to pay for the encoder
     if (m->gather == RTC_GATHER_P2P && m->n > 1 && !m->calibrated && !m->user_bands && m->n_col >= 3) {
         const uint32_t rows0 = m->last_rows[1] - m->last_rows[0];
-        const float band_ms = m->last_ms[0] - m->last_enc_ms;
+        const float band_ms = m->last_own_ms;
         if (rows0 > 0 && band_ms > 0.f) m->deficit_rows = (double)m->last_enc_ms / ((double)band_ms / (double)rows0);
         m->calibrated = true;
     }
@@ -826,6 +832,7 @@ int rtc_mgpu_collect(rtc_mgpu* m, const char** host_ptr, size_t* n_bytes)
     size_t total = 0;
     for (int g = 0; g < m->n; ++g) { total += (size_t)f.len[g]; m->last_ms[g] = f.ms[g]; }
     m->last_enc_ms = f.enc_ms;
+    m->last_own_ms = f.own_ms;
     memcpy(m->last_rows, f.rows, sizeof(uint32_t) * (m->n + 1));
     *host_ptr = f.host;
     *n_bytes = total;
