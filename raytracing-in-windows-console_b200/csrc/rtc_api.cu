@@ -125,28 +125,38 @@ int upload_scene(rtc_ctx* c)
     const size_t b_objs = (n * sizeof(rtc_object) + 63) & ~(size_t)63, b_sph = (n_slots * sizeof(int32_t) + 63) & ~(size_t)63,
                  b_pl = (c->plane_obj.size() * sizeof(int32_t) + 63) & ~(size_t)63;
     const size_t b_all = b_objs + b_sph + b_pl + 64;
-    if (b_all > c->d_scene.cap) {
-        CK(cudaStreamSynchronize(c->stream));                   // (the host copy is authoritative here: nothing to keep)
-        CK(c->d_scene.ensure(b_all * 2));
+    // Next ring slot: stage in pinned memory, copy on the upload stream, make the frame stream wait for the copy.
+    const int b = (c->scene_cur + 1) % rtc_ctx::kSceneRing;
+    if (c->scene_up_pending[b]) {                               // the previous upload out of this staging slot (4 uploads ago)
+        CK(cudaEventSynchronize(c->ev_scene_up[b]));
+        c->scene_up_pending[b] = false;
     }
-    c->d_objs.p = reinterpret_cast<rtc_object*>(c->d_scene.p);
-    c->d_sphere_obj.p = reinterpret_cast<int32_t*>(c->d_scene.p + b_objs);
-    c->d_plane_obj.p = reinterpret_cast<int32_t*>(c->d_scene.p + b_objs + b_sph);
-    c->scene_slot ^= 1;
-    PinBuf<unsigned char>& st = c->h_scene[c->scene_slot];
-    if (c->scene_pending[c->scene_slot]) {                      // an earlier upload may still be reading this slot
-        CK(cudaEventSynchronize(c->ev_scene[c->scene_slot]));
-        c->scene_pending[c->scene_slot] = false;
-    }
+    PinBuf<unsigned char>& st = c->h_scene[b];
     if (b_all > st.cap) CK(st.ensure(b_all * 2));
+    if (b_all > c->d_scene[b].cap) CK(c->d_scene[b].ensure(b_all * 2));   // (cudaFree synchronises the device: nothing still reads the old block)
     unsigned char* h = st.p;
     if (n) memcpy(h, c->objs.data(), n * sizeof(rtc_object));
     if (!c->sphere_obj.empty()) memcpy(h + b_objs, c->sphere_obj.data(), c->sphere_obj.size() * sizeof(int32_t));
     if (!c->plane_obj.empty()) memcpy(h + b_objs + b_sph, c->plane_obj.data(), c->plane_obj.size() * sizeof(int32_t));
-    CK(cudaMemcpyAsync(c->d_scene.p, h, b_all - 64, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaEventRecord(c->ev_scene[c->scene_slot], c->stream));
-    c->scene_pending[c->scene_slot] = true;
+    if (c->scene_rd_recorded[b]) CK(cudaStreamWaitEvent(c->upload_stream, c->ev_scene_rd[b], 0));   // frames still reading this device slot
+    CK(cudaMemcpyAsync(c->d_scene[b].p, h, b_all - 64, cudaMemcpyHostToDevice, c->upload_stream));
+    CK(cudaEventRecord(c->ev_scene_up[b], c->upload_stream));
+    c->scene_up_pending[b] = true;
+    CK(cudaStreamWaitEvent(c->stream, c->ev_scene_up[b], 0));
+    c->scene_cur = b;
+    c->d_objs.p = reinterpret_cast<rtc_object*>(c->d_scene[b].p);
+    c->d_sphere_obj.p = reinterpret_cast<int32_t*>(c->d_scene[b].p + b_objs);
+    c->d_plane_obj.p = reinterpret_cast<int32_t*>(c->d_scene[b].p + b_objs + b_sph);
     c->scene_dirty = false;
+    return RTC_OK;
+}
+
+// Everything enqueued so far on the frame stream may read the current scene slot: the upload stream must not overwrite it
+// before this point of the frame stream has been reached.
+int mark_scene_read(rtc_ctx* c)
+{
+    CK(cudaEventRecord(c->ev_scene_rd[c->scene_cur], c->stream));
+    c->scene_rd_recorded[c->scene_cur] = true;
     return RTC_OK;
 }
 
@@ -304,7 +314,7 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
         CK(cudaEventRecord(c->ev[2], c->stream));
         CK(cudaEventRecord(c->ev[3], c->stream));
     }
-    return RTC_OK;
+    return mark_scene_read(c);
 }
 
 }  // namespace rtc
@@ -364,7 +374,9 @@ int rtc_create(rtc_ctx** out, int device)
     CKC(c->d_total.ensure(2));
     CKC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (auto& ev : c->ev_total) CKC(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    for (auto& ev : c->ev_scene) CKC(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto& ev : c->ev_scene_up) CKC(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto& ev : c->ev_scene_rd) CKC(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CKC(cudaStreamCreateWithFlags(&c->upload_stream, cudaStreamNonBlocking));
     CKC(c->d_sink.ensure(4));
     CKC(c->h_total.ensure(2));
 #undef CKC
@@ -377,15 +389,18 @@ void rtc_destroy(rtc_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
-    c->d_scene.release(); c->d_fast.release(); c->d_exact.release();
+    if (c->upload_stream) { cudaStreamSynchronize(c->upload_stream); cudaStreamDestroy(c->upload_stream); }
+    for (auto& b : c->d_scene) b.release();
+    c->d_fast.release(); c->d_exact.release();
     c->d_fast_l.release(); c->d_exact_l.release(); c->d_shadow.release(); c->d_kd.release(); c->d_dmin.release(); c->d_dmin_l.release();
     c->d_cone.release(); c->d_cone_l.release(); c->d_sin.release(); c->d_sin_l.release();
     c->d_hit_t.release(); c->d_hit_idx.release(); c->d_color.release(); c->d_glyph.release(); c->d_out[0].release(); c->d_out[1].release();
     c->d_desc.release(); c->d_counters.release(); c->d_total.release(); c->d_sink.release();
-    c->h_total.release(); c->h_out[0].release(); c->h_out[1].release(); c->h_scene[0].release(); c->h_scene[1].release();
+    c->h_total.release(); c->h_out[0].release(); c->h_out[1].release(); for (auto& b : c->h_scene) b.release();
     c->h_color.release(); c->h_glyph.release();
     for (auto& ev : c->ev_total) if (ev) cudaEventDestroy(ev);
-    for (auto& ev : c->ev_scene) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c->ev_scene_up) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c->ev_scene_rd) if (ev) cudaEventDestroy(ev);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     c->h_hit_t.release(); c->h_hit_idx.release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
@@ -521,7 +536,7 @@ int rtc_update_objects(rtc_ctx* c, double dt, uint32_t flags)
     if (rc) return rc;
     CK(rtc::launch_update_objects(c->stream, c->d_objs.p, (int)n, dt));
     c->host_stale = true;
-    return RTC_OK;
+    return mark_scene_read(c);
 }
 
 // ---- frame ------------------------------------------------------------------------------------

@@ -77,7 +77,16 @@ struct rtc_ctx {
     bool scene_dirty = true;       // host -> device upload pending
     bool host_stale = false;       // device physics ran; host copy must be refreshed before use
     // device scene: ONE blob [objects | sphere index list | plane index list] so that an upload is a single copy
-    rtc::DevBuf<unsigned char> d_scene;
+    // (a ring: the upload of the NEXT scene runs on its own stream, ahead of and beside the kernels of the frames in flight,
+    //  so a per-frame scene upload is never on a frame's critical path -- in-stream it waited behind the D2H traffic of
+    //  the previous frame's stream on the same PCIe link)
+    static constexpr int kSceneRing = 4;
+    rtc::DevBuf<unsigned char> d_scene[kSceneRing];
+    int scene_cur = 0;                               // ring slot the views below point into
+    cudaStream_t upload_stream = nullptr;
+    cudaEvent_t ev_scene_up[kSceneRing] = {};        // the upload into ring slot i has finished (upload stream)
+    cudaEvent_t ev_scene_rd[kSceneRing] = {};        // everything enqueued so far that reads ring slot i has finished (frame stream)
+    bool scene_up_pending[kSceneRing] = {}, scene_rd_recorded[kSceneRing] = {};
     struct View { rtc_object* p = nullptr; } d_objs;
     struct ViewI { int32_t* p = nullptr; } d_sphere_obj, d_plane_obj;
     rtc::DevBuf<float> d_fast;      // 12 B per sphere slot (slots padded to a multiple of 4)
@@ -103,10 +112,7 @@ struct rtc_ctx {
     rtc::DevBuf<float> d_sink;
     rtc::PinBuf<unsigned long long> h_total;     // [2]
     rtc::PinBuf<char> h_out[2];
-    rtc::PinBuf<unsigned char> h_scene[2];       // pinned staging of the scene upload (objects + index lists)
-    int scene_slot = 0;
-    cudaEvent_t ev_scene[2] = {nullptr, nullptr};   // the H2D copy out of staging slot i has finished
-    bool scene_pending[2] = {false, false};
+    rtc::PinBuf<unsigned char> h_scene[kSceneRing];   // pinned staging of the scene upload (objects + index lists), one per ring slot
     cudaStream_t copy_stream = nullptr;     // D2H of finished streams, concurrent with the next frame's kernels
     cudaEvent_t ev_total[2] = {nullptr, nullptr};   // slot's encode finished and its length is on the host
     int cur = 0;                            // slot of the last rtc_render
