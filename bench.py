@@ -433,10 +433,11 @@ def run_ours(args):
         dist.barrier()
         torch.cuda.synchronize()
         if rank != 0:
-            dist.barrier(group=gloo)                            # rank 0 has finished measuring
+            dist.barrier(group=gloo)                            # rank 0 has finished the headline measurement
             tt = torch.zeros(2, dtype=torch.float64, device=torch.device("cuda", local_rank))
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dist.destroy_process_group()
+            dist.barrier(group=gloo)                            # rank 0 has finished the sub-records too: only now tear the
+            dist.destroy_process_group()                        # CUDA contexts on the other GPUs down (it disturbs short timings)
             return
 
     mode = rtc_b200.MODE_NAMES.index(args.mode)
@@ -661,6 +662,7 @@ def run_ours(args):
     ctx.close()
     ok = line.get("parity_check", {}).get("n_gpu_equals_1_gpu", True)
     if dist is not None:
+        dist.barrier(group=gloo)
         dist.destroy_process_group()
     if not ok:
         raise SystemExit("N-GPU stream differs from the single-GPU stream: %r" % (line["parity_check"],))

@@ -132,8 +132,17 @@ int upload_scene(rtc_ctx* c)
         c->scene_up_pending[b] = false;
     }
     PinBuf<unsigned char>& st = c->h_scene[b];
-    if (b_all > st.cap) CK(st.ensure(b_all * 2));
-    if (b_all > c->d_scene[b].cap) CK(c->d_scene[b].ensure(b_all * 2));   // (cudaFree synchronises the device: nothing still reads the old block)
+    if (b_all > st.cap || b_all > c->d_scene[b].cap) {
+        // grow EVERY ring slot now (a scene that grows keeps growing slot by slot otherwise: four allocation stalls instead
+        // of one); cudaFree / cudaFreeHost synchronise the device, so nothing still reads the old blocks -- but the slots in
+        // flight hold live scenes, so only slots other than the current one may be replaced before their turn
+        for (int i = 0; i < rtc_ctx::kSceneRing; ++i) {
+            if (i == c->scene_cur) continue;
+            if (c->scene_up_pending[i]) { CK(cudaEventSynchronize(c->ev_scene_up[i])); c->scene_up_pending[i] = false; }
+            if (b_all > c->h_scene[i].cap) CK(c->h_scene[i].ensure(b_all * 2));
+            if (b_all > c->d_scene[i].cap) { CK(cudaStreamSynchronize(c->stream)); CK(c->d_scene[i].ensure(b_all * 2)); }
+        }
+    }
     unsigned char* h = st.p;
     if (n) memcpy(h, c->objs.data(), n * sizeof(rtc_object));
     if (!c->sphere_obj.empty()) memcpy(h + b_objs, c->sphere_obj.data(), c->sphere_obj.size() * sizeof(int32_t));
