@@ -133,14 +133,15 @@ int upload_scene(rtc_ctx* c)
     }
     PinBuf<unsigned char>& st = c->h_scene[b];
     if (b_all > st.cap || b_all > c->d_scene[b].cap) {
-        // grow EVERY ring slot now (a scene that grows keeps growing slot by slot otherwise: four allocation stalls instead
-        // of one); cudaFree / cudaFreeHost synchronise the device, so nothing still reads the old blocks -- but the slots in
-        // flight hold live scenes, so only slots other than the current one may be replaced before their turn
+        // Grow EVERY ring slot now, in one stall (pinned allocations synchronise every device of the process; a scene that
+        // grows would otherwise stall four times, once per slot).  After the two synchronisations nothing reads any slot,
+        // and the current slot's contents are dead: this upload replaces the scene (the host copy is authoritative here).
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaStreamSynchronize(c->upload_stream));
         for (int i = 0; i < rtc_ctx::kSceneRing; ++i) {
-            if (i == c->scene_cur) continue;
-            if (c->scene_up_pending[i]) { CK(cudaEventSynchronize(c->ev_scene_up[i])); c->scene_up_pending[i] = false; }
+            c->scene_up_pending[i] = false;
             if (b_all > c->h_scene[i].cap) CK(c->h_scene[i].ensure(b_all * 2));
-            if (b_all > c->d_scene[i].cap) { CK(cudaStreamSynchronize(c->stream)); CK(c->d_scene[i].ensure(b_all * 2)); }
+            if (b_all > c->d_scene[i].cap) CK(c->d_scene[i].ensure(b_all * 2));
         }
     }
     unsigned char* h = st.p;
