@@ -294,7 +294,7 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
                                  c->d_cone.p + s0 / 4, c->d_sin.p + s0 / 4, c->d_sphere_obj.p + s0,
                                  sph, slots, c->d_objs.p, c->d_plane_obj.p, last ? n_planes : 0, c->d_hit_t.p,
                                  c->d_hit_idx.p, c->d_counters.p + ch, ch > 0 ? 1 : 0, nullptr, nullptr, plan.threads, cull, stats,
-                                 c->shade, fused && last ? shade_mode : -1, d_color, d_glyph, !last || keep_hits, c->d_kd.p, affine));
+                                 c->shade, fused && last ? shade_mode : -1, d_color, d_glyph, !last || keep_hits, c->d_kd.p, affine, plan.rays));
             c->last_launches++;
         }
         c->hits_valid = keep_hits;
@@ -309,7 +309,7 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
                                      c->d_dmin_l.p + s0 / 4, c->d_cone_l.p + s0 / 4, c->d_sin_l.p + s0 / 4, c->d_sphere_obj.p + s0, sph, slots,
                                      c->d_objs.p, c->d_plane_obj.p, last ? n_planes : 0,
                                      c->d_hit_t.p, c->d_hit_idx.p, c->d_counters.p + 32 + ch, ch > 0 ? 1 : 0, c->shade.light,
-                                     c->d_shadow.p, plan.threads, cull, stats + 1, c->shade, -1, nullptr, nullptr, false, nullptr, false));
+                                     c->d_shadow.p, plan.threads, cull, stats + 1, c->shade, -1, nullptr, nullptr, false, nullptr, false, plan.rays));
                 c->last_launches++;
             }
         }
@@ -709,7 +709,7 @@ int rtc_last_timings(rtc_ctx* c, rtc_timings* out)
     unsigned long long groups[2] = {0ull, 0ull};
     CK(cudaMemcpyAsync(groups, c->d_counters.p + rtc::kStatsCounter, sizeof groups, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    out->sphere_tests = (groups[0] + groups[1]) * 4ull * 256ull;
+    out->sphere_tests = (groups[0] + groups[1]) * 4ull * 32ull;        // the kernel counts groups x rays per thread
     return RTC_OK;
 }
 

@@ -11,7 +11,7 @@ struct FrameParams;
 struct ShadeParams;
 
 // The persistent ray-kernel CTA (one per SM) exists with 24 and with 28 warps; plan_trace picks per launch.
-struct TracePlan { int threads; int max_slots; };   // threads per CTA; sphere slots resident in shared memory per launch
+struct TracePlan { int threads; int max_slots; int rays; };   // threads per CTA; sphere slots resident in shared memory per launch; rays per thread (8 or 4)
 TracePlan plan_trace(uint32_t x, uint32_t rows, int n_slots, int n_ctas);
 constexpr int kNumCounters = 64;           // per-frame device counters zeroed by the hoist kernel
 constexpr int kMaxChunks = 28;             // sphere-list chunks per pass (one tile ticket each): 69k spheres at 24 warps
@@ -19,7 +19,7 @@ constexpr int kStatsCounter = 60;          // [60..63]: two 64-bit counts of sph
 
 // kernel 0 / 1 (rtc_trace.cu)
 cudaError_t configure_trace();
-size_t trace_smem_bytes(int n_slots, int threads);
+size_t trace_smem_bytes(int n_slots, int threads, int rays);
 cudaError_t launch_hoist(cudaStream_t st, const rtc_object* objs, const int32_t* sphere_obj, int n_spheres,
                          int n_slots, const float cam[3], float* sph_fast, float4* sph_exact, float* grp_dmin,
                          float4* grp_cone, float* grp_sin, unsigned int* counters, int n_counters,
@@ -32,7 +32,7 @@ cudaError_t launch_trace(cudaStream_t st, int n_ctas, const FrameParams& fp, con
                          uint8_t* shadow, int threads, bool cull, unsigned long long* groups_tested,
                          const ShadeParams& sp, int shade_mode /* >= 0: shade + quantise in the tile epilogue; -1: no */,
                          uint8_t* color, uint8_t* glyph, bool write_hits, const float4* obj_kd /* per object colour / 255 */,
-                         bool affine /* g_fast is in the screen-affine layout (primary rays only) */);
+                         bool affine /* g_fast is in the screen-affine layout (primary rays only) */, int rays /* per thread: 8 or 4 */);
 
 // kernel 2 (rtc_shade.cu): stand-alone shade + quantise, used only after a shadow pass
 cudaError_t launch_shade(cudaStream_t st, const FrameParams& fp, const ShadeParams& sp, int mode,

@@ -159,10 +159,14 @@ hoist_kernel(const rtc_object* __restrict__ objs, const int32_t* __restrict__ sp
 }
 
 // ---- kernel 1: trace --------------------------------------------------------------------
-constexpr int kRays = 8;            // rays per thread
+// Rays per thread are a template parameter (kRays = 8 or 4): a thread owns one column and kRays rows (every other row) of
+// its warp's 16 x 2*kRays tile.  8 is the efficient shape (the per-column operand F of the screen-affine filter is
+// amortised over 8 tests); 4 halves the work quantum for launches of only one or two tile waves (an 8-GPU band of a 4K
+// frame), where the phases of a warp's single tile -- ray set-up, sphere loop, shading epilogue -- would otherwise run in
+// lock step on all warps and not overlap (plan_trace).
 // Threads per CTA are a template parameter (compile-time state stride; a run-time stride cost 3 %): 768 (24 warps,
 // 80 registers) and 896 (28 warps, 72 registers) are instantiated and plan_trace picks per launch.
-constexpr int kTile = 16;           // warp tile = 16 x 16 pixels
+constexpr int kTile = 16;           // warp tile = 16 columns x 2*kRays rows
 
 // Shared-memory layout (dynamic): [exact float4 x n_slots][fast 12 B x n_slots][group dmin 4 B x n_slots/4][state]
 // state, each [kRays][blockDim.x]: best_t, best_idx, divTwoA, and the exact ray direction
@@ -191,7 +195,7 @@ struct Smem {
     float* dirz;
     struct ShadeCtx* shade;   // tile epilogue: light / material block, camera, mode (one per CTA)
 };
-__device__ __forceinline__ Smem carve(unsigned char* raw, int n_slots, int n_threads)
+__device__ __forceinline__ Smem carve(unsigned char* raw, int n_slots, int n_threads, int n_rays)
 {
     Smem s;
     s.exact = reinterpret_cast<float4*>(raw);
@@ -201,7 +205,7 @@ __device__ __forceinline__ Smem carve(unsigned char* raw, int n_slots, int n_thr
     s.gdmin = reinterpret_cast<float*>(s.gcone + ng4);
     s.gsin = s.gdmin + ng4;
     float* st = s.gsin + ng4;
-    const int n = kRays * n_threads;
+    const int n = n_rays * n_threads;
     s.best_t = st;
     s.best_idx = reinterpret_cast<int*>(st + n);
     s.div2A = st + 2 * n;
@@ -232,11 +236,11 @@ __device__ __forceinline__ float4 lds128(uint32_t addr)
 // order-independently as the lexicographic minimum of (distance, object index).
 // A cheap, rigorous lower bound of the hit distance skips candidates that cannot beat the
 // running best (most of them: a ray pierces ~N/100 spheres but only the nearest matters).
-template <int kThreads>
+template <int kThreads, int kRays>
 __device__ __noinline__ void exact_group(const int32_t* __restrict__ sphere_obj, int n_slots, int g, uint32_t mask, int tid)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const Smem s = carve(smem_raw, n_slots, kThreads);
+    const Smem s = carve(smem_raw, n_slots, kThreads, kRays);
     while (mask) {
         const int b = __ffs(mask) - 1;
         mask &= mask - 1;
@@ -288,7 +292,7 @@ __device__ __noinline__ uint32_t shade_call(const ShadeCtx* __restrict__ sc, flo
 //   A thread's 8 rays share their column, i.e. vx: F = C + vx A is ONE packed op per sphere pair and thread, and a test
 //   is t = F + vy_r B, u = t (2^64 / |w_r|) -- 2 packed ops per pair + the sticky accumulate: 50 packed ops per group
 //   instead of 64.  The operands of the dot-product form (ex, ey, ez) become (vx, vy_r, 2^64 / |w_r|) here.
-template <int kThreads, bool AFFINE>
+template <int kThreads, bool AFFINE, int kRays>
 __device__ __forceinline__ void test_group(const Smem& s, uint32_t fa, int g, const float (&ex)[kRays], const float (&ey)[kRays],
                                            const float (&ez)[kRays], const int32_t* __restrict__ sphere_obj, int n_slots, int tid)
 {
@@ -357,7 +361,7 @@ __device__ __forceinline__ void test_group(const Smem& s, uint32_t fa, int g, co
 #pragma unroll
             for (int r = 0; r < kRays; ++r)
                 if (gd > s.best_t[r * kThreads + tid]) mask &= ~(0x00030003u << (2 * r));
-            if (mask) exact_group<kThreads>(sphere_obj, n_slots, g, mask, tid);
+            if (mask) exact_group<kThreads, kRays>(sphere_obj, n_slots, g, mask, tid);
         }
     }
 }
@@ -372,7 +376,7 @@ __device__ __forceinline__ void test_group(const Smem& s, uint32_t fa, int g, co
 // CULL = true (RTC_FLAG_CULL): per warp tile, the groups of 4 spheres whose bounding cone (hoisted) misses the tile's
 //   ray cone are skipped -- results are identical, far fewer tests are executed (the count is reported).
 // AFFINE = true: the screen-affine packed filter (see test_group); primary rays only.
-template <bool SHADOW, int kThreads, bool CULL, bool AFFINE>
+template <bool SHADOW, int kThreads, bool CULL, bool AFFINE, int kRays>
 __global__ void __launch_bounds__(kThreads, 1)
 trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float4* __restrict__ g_exact,
              const float* __restrict__ g_dmin, const float4* __restrict__ g_cone, const float* __restrict__ g_sin,
@@ -385,7 +389,8 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
              uint8_t* __restrict__ color, uint8_t* __restrict__ glyph, int write_hits, const float4* __restrict__ obj_kd)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const Smem s = carve(smem_raw, n_slots, kThreads);
+    const Smem s = carve(smem_raw, n_slots, kThreads, kRays);
+    constexpr uint32_t kTileH = 2u * kRays;                      // tile height in rows
     const int tid = threadIdx.x, lane = tid & 31;
     if (!SHADOW && tid == 0) {
         ShadeCtx* sc = s.shade;
@@ -405,7 +410,7 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
 
     const uint32_t W = fp.x - 1u;
     const uint32_t rows = fp.row1 - fp.row0;
-    const uint32_t tiles_x = (W + kTile - 1) / kTile, tiles_y = (rows + kTile - 1) / kTile;
+    const uint32_t tiles_x = (W + kTile - 1) / kTile, tiles_y = (rows + kTileH - 1) / kTileH;
     const uint32_t n_tiles = tiles_x * tiles_y;
     const int n_groups = n_slots >> 2;
     const V3 cam = v3(fp.cam[0], fp.cam[1], fp.cam[2]);
@@ -425,7 +430,7 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
         float ex[kRays], ey[kRays], ez[kRays];            // ray direction scaled by 2^64 (exact)
 #pragma unroll
         for (int r = 0; r < kRays; ++r) {
-            uint32_t row = fp.row0 + ty * kTile + py + 2u * r;
+            uint32_t row = fp.row0 + ty * kTileH + py + 2u * r;
             if (row >= fp.row1) row = fp.row1 - 1u;
             float vx, vy, inv;
             V3 d = initial_direction_ex(fp, row, colc, vx, vy, inv);
@@ -471,7 +476,7 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
             if (!__any_sync(0xffffffffu, any)) {
 #pragma unroll
                 for (int r = 0; r < kRays; ++r) {
-                    const uint32_t row = fp.row0 + ty * kTile + py + 2u * r;
+                    const uint32_t row = fp.row0 + ty * kTileH + py + 2u * r;
                     if (row < fp.row1 && col < W && !carry_in) shadow[(size_t)(row - fp.row0) * W + col] = 0;
                 }
                 continue;
@@ -482,7 +487,7 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
         if (!CULL) {
             uint32_t fa = fast_base;
 #pragma unroll 2
-            for (int g = 0; g < n_groups; ++g, fa += 48u) test_group<kThreads, AFFINE>(s, fa, g, ex, ey, ez, sphere_obj, n_slots, tid);
+            for (int g = 0; g < n_groups; ++g, fa += 48u) test_group<kThreads, AFFINE, kRays>(s, fa, g, ex, ey, ez, sphere_obj, n_slots, tid);
             my_groups += (unsigned int)n_groups;
         } else {
             // Bounding cone of this warp's (active) rays: axis = normalised sum of the directions, cos(theta) = the
@@ -531,11 +536,11 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
                 while (m) {
                     const int g0 = gb + __ffs(m) - 1;
                     m &= m - 1;
-                    test_group<kThreads, AFFINE>(s, fast_base + 48u * (uint32_t)g0, g0, ex, ey, ez, sphere_obj, n_slots, tid);
+                    test_group<kThreads, AFFINE, kRays>(s, fast_base + 48u * (uint32_t)g0, g0, ex, ey, ez, sphere_obj, n_slots, tid);
                     if (m) {                                     // a second group back to back: the unroll-by-2 of the brute-force loop
                         const int g1 = gb + __ffs(m) - 1;
                         m &= m - 1;
-                        test_group<kThreads, AFFINE>(s, fast_base + 48u * (uint32_t)g1, g1, ex, ey, ez, sphere_obj, n_slots, tid);
+                        test_group<kThreads, AFFINE, kRays>(s, fast_base + 48u * (uint32_t)g1, g1, ex, ey, ez, sphere_obj, n_slots, tid);
                     }
                 }
             }
@@ -563,7 +568,7 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
         if (SHADOW || write_hits) {
 #pragma unroll
             for (int r = 0; r < kRays; ++r) {
-                const uint32_t row = fp.row0 + ty * kTile + py + 2u * r;
+                const uint32_t row = fp.row0 + ty * kTileH + py + 2u * r;
                 if (row < fp.row1 && col < W) {
                     const size_t pix = (size_t)(row - fp.row0) * W + col;
                     const int slot = r * kThreads + tid;
@@ -596,7 +601,7 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
                 const int idx = s.best_idx[slot];
                 uint32_t v = (bit8 ? 16u : 0u) | ((uint32_t)' ' << 24);
                 if (t <= fp.far_dist) v = shade_call(s.shade, s.dirx[slot], s.diry[slot], s.dirz[slot], t, idx);
-                const uint32_t row = fp.row0 + ty * kTile + py + 2u * r;
+                const uint32_t row = fp.row0 + ty * kTileH + py + 2u * r;
                 if (fast) {
                     unsigned char* run = reinterpret_cast<unsigned char*>(s.div2A + r * kThreads + (tid & ~31));
                     unsigned char* pc = run + (py * 16u + px) * bpp;
@@ -612,9 +617,9 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
             }
             if (fast) {                                          // W % 16 == 0: every tile is 16 columns wide
                 __syncwarp();
-                const uint32_t row_t = fp.row0 + ty * kTile;     // first row of the tile
+                const uint32_t row_t = fp.row0 + ty * kTileH;    // first row of the tile
                 const uint32_t parts = bpp;                      // 16-byte pieces per tile row: 3 (RGB) or 1 (index)
-                for (uint32_t i = (uint32_t)lane; i < 16u * parts; i += 32u) {
+                for (uint32_t i = (uint32_t)lane; i < kTileH * parts; i += 32u) {
                     const uint32_t rho = i / parts, part = i - rho * parts;      // tile row, piece
                     const uint32_t row = row_t + rho;
                     if (row < fp.row1) {
@@ -623,7 +628,7 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
                         *reinterpret_cast<uint4*>(color + ((size_t)(row - fp.row0) * W + tx * kTile) * bpp + part * 16u) = q;
                     }
                 }
-                if (has_gl && lane < 16) {
+                if (has_gl && lane < (int)kTileH) {
                     const uint32_t row = row_t + (uint32_t)lane;
                     if (row < fp.row1) {
                         const unsigned char* run = reinterpret_cast<const unsigned char*>(s.div2A + (lane >> 1) * kThreads + (tid & ~31));
@@ -635,52 +640,62 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
             }
         }
     }
-    if (lane == 0 && groups_tested != nullptr && my_groups) atomicAdd(groups_tested, (unsigned long long)my_groups);
+    if (lane == 0 && groups_tested != nullptr && my_groups) atomicAdd(groups_tested, (unsigned long long)my_groups * kRays);   // x 4 spheres x 32 lanes = tests
 }
 
 cudaError_t configure_trace()   // per device, once per context
 {
     cudaError_t e;
-#define RTC_TRACE_ATTR(SH, T, C, A)                                                                                          \
-    if ((e = cudaFuncSetAttribute(trace_kernel<SH, T, C, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e
+#define RTC_TRACE_ATTR1(SH, T, C, A, R)                                                                                      \
+    if ((e = cudaFuncSetAttribute(trace_kernel<SH, T, C, A, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e
+#define RTC_TRACE_ATTR(SH, T, C, A) RTC_TRACE_ATTR1(SH, T, C, A, 8); RTC_TRACE_ATTR1(SH, T, C, A, 4)
     RTC_TRACE_ATTR(false, 768, false, false); RTC_TRACE_ATTR(true, 768, false, false); RTC_TRACE_ATTR(false, 896, false, false); RTC_TRACE_ATTR(true, 896, false, false);
     RTC_TRACE_ATTR(false, 768, true, false);  RTC_TRACE_ATTR(true, 768, true, false);  RTC_TRACE_ATTR(false, 896, true, false);  RTC_TRACE_ATTR(true, 896, true, false);
     RTC_TRACE_ATTR(false, 768, false, true);  RTC_TRACE_ATTR(false, 896, false, true); RTC_TRACE_ATTR(false, 768, true, true);   RTC_TRACE_ATTR(false, 896, true, true);
 #undef RTC_TRACE_ATTR
+#undef RTC_TRACE_ATTR1
     return cudaSuccess;
 }
 
-size_t trace_smem_bytes(int n_slots, int threads)
+size_t trace_smem_bytes(int n_slots, int threads, int rays)
 {
     return (size_t)n_slots * 28 + (size_t)(((n_slots >> 2) + 3) & ~3) * 24 +     // spheres, per-group bounds (4 + 16 + 4 B),
-           (size_t)threads * (6 * kRays * 4) + 96;                                // best_t, best_idx, div2A, dir x/y/z; ShadeCtx
+           (size_t)threads * (6 * rays * 4) + 96;                                 // best_t, best_idx, div2A, dir x/y/z; ShadeCtx
 }
 
-// Threads per CTA and sphere slots per launch for a band of `rows` rows.
-// A warp's work quantum is one 256-ray tile, so T tiles take ceil(T / (CTAs * warps)) tile times, and a tile time is
-// warps / throughput(warps).  With many waves 24 and 28 warps are equally fast (config 3: 1.2056 / 1.2078 ms; 16
-// warps: 1.2677), but an 8-GPU band of a 4K frame is 4080 tiles = 27.6 per SM: 28 warps finish it in ONE wave
-// (0.198 ms against 0.259 with 24, 0.230 with 16 -- profiles/r01_trace_kernel_ncu.md).  More warps leave less
-// shared memory for spheres, i.e. more launches over a long sphere list -- priced in per chunk.
+// Threads per CTA, rays per thread and sphere slots per launch for a band of `rows` rows.
+// A warp's work quantum is one tile (16 x 2*rays pixels), so T tiles take ceil(T / (CTAs * warps)) tile times, and a tile
+// time is warps / throughput(warps).  With many waves 24 and 28 warps are equally fast, but an 8-GPU band of a 4K frame
+// is 4080 tiles of 16 x 16 = 27.6 per SM: 28 warps finish it in ONE wave (profiles/r01_trace_kernel_ncu.md).  In a
+// launch of one or two waves, though, every warp is in the same phase of its tile at the same time -- ray set-up, sphere
+// loop, shading epilogue -- and set-up and epilogue (a quarter of a tile's time) overlap nothing; hence the constant
+// added to the wave count below, and hence 16 x 8 tiles (4 rays per thread; the sphere loop costs 4 % more per test) for
+// small launches: twice the waves of half the length.  More warps or rays leave less shared memory for spheres, i.e. more
+// launches over a long sphere list -- priced in per chunk.
 TracePlan plan_trace(uint32_t x, uint32_t rows, int n_slots, int n_ctas)
 {
     static const char* force = getenv("RTC_TRACE_THREADS_FORCE");      // experiments only
+    static const char* force_rays = getenv("RTC_TRACE_RAYS_FORCE");
     const long long W = (long long)x - 1;
-    const long long tiles = ((W + kTile - 1) / kTile) * (((long long)rows + kTile - 1) / kTile);
-    TracePlan best{896, 0};
+    TracePlan best{896, 0, 8};
     double best_cost = -1.0;
-    for (int w = 28; w >= 24; w -= 4) {                                // ties go to 28 warps
-        if (force && atoi(force) != w * 32) continue;
-        const int max_slots = (int)((227 * 1024 - 192 - (long long)w * 32 * (6 * kRays * 4)) / 34) & ~3;
-        const int chunks = n_slots <= max_slots ? 1 : (n_slots + max_slots - 1) / max_slots;
-        if (chunks > kMaxChunks && w > 24) continue;                   // (the API refuses more chunks than it has tickets for)
-        const long long per_wave = (long long)n_ctas * w;
-        const double waves = (double)((tiles + per_wave - 1) / per_wave);
-        // per chunk: the sphere loop over its share of the list + a fixed ray set-up / write-back worth ~40 sphere tests
-        const double cost = waves * w * ((double)(n_slots > 0 ? n_slots : 1) + 40.0 * chunks);
-        if (best_cost < 0.0 || cost < best_cost) { best_cost = cost; best.threads = w * 32; best.max_slots = max_slots; }
+    for (int rays = 8; rays >= 4; rays -= 4) {                         // ties go to 8 rays, then to 28 warps
+        if (force_rays && atoi(force_rays) != rays) continue;
+        const long long tiles = ((W + kTile - 1) / kTile) * (((long long)rows + 2 * rays - 1) / (2 * rays));
+        for (int w = 28; w >= 24; w -= 4) {
+            if (force && atoi(force) != w * 32) continue;
+            const int max_slots = (int)((227 * 1024 - 192 - (long long)w * 32 * (6 * rays * 4)) / 34) & ~3;
+            const int chunks = n_slots <= max_slots ? 1 : (n_slots + max_slots - 1) / max_slots;
+            if (chunks > kMaxChunks && w > 24) continue;               // (the API refuses more chunks than it has tickets for)
+            const long long per_wave = (long long)n_ctas * w;
+            const double waves = (double)((tiles + per_wave - 1) / per_wave);
+            // per chunk: the sphere loop over its share of the list + a fixed ray set-up / write-back worth ~40 sphere tests
+            const double tile_time = w * rays * ((double)(n_slots > 0 ? n_slots : 1) * (rays == 4 ? 1.04 : 1.0) + 40.0 * chunks);
+            const double cost = (waves + 0.25) * tile_time;
+            if (best_cost < 0.0 || cost < best_cost * 0.999) { best_cost = cost; best.threads = w * 32; best.max_slots = max_slots; best.rays = rays; }
+        }
     }
-    if (best.max_slots == 0) best.max_slots = (int)((227 * 1024 - 192 - (long long)best.threads * (6 * kRays * 4)) / 34) & ~3;
+    if (best.max_slots == 0) best.max_slots = (int)((227 * 1024 - 192 - (long long)best.threads * (6 * best.rays * 4)) / 34) & ~3;
     return best;
 }
 
@@ -710,15 +725,17 @@ cudaError_t launch_trace(cudaStream_t st, int n_ctas, const FrameParams& fp, con
                          int n_slots, const rtc_object* objs, const int32_t* plane_obj, int n_planes, float* hit_t,
                          int32_t* hit_idx, unsigned int* tile_counter, int carry_in, const float* light, uint8_t* shadow,
                          int threads, bool cull, unsigned long long* groups_tested, const ShadeParams& sp, int shade_mode,
-                         uint8_t* color, uint8_t* glyph, bool write_hits, const float4* obj_kd, bool affine)
+                         uint8_t* color, uint8_t* glyph, bool write_hits, const float4* obj_kd, bool affine, int rays)
 {
-    const size_t smem = trace_smem_bytes(n_slots, threads);
+    const size_t smem = trace_smem_bytes(n_slots, threads, rays);
     const float l0 = light ? light[0] : 0.f, l1 = light ? light[1] : 0.f, l2 = light ? light[2] : 0.f;
+#define RTC_TRACE_LAUNCH1(SH, T, C, A, R)                                                                                \
+    trace_kernel<SH, T, C, A, R><<<n_ctas, T, smem, st>>>(fp, g_fast, g_exact, g_dmin, g_cone, g_sin, sphere_obj, n_spheres, \
+                                                          n_slots, objs, plane_obj, n_planes, hit_t, hit_idx, tile_counter, \
+                                                          carry_in, l0, l1, l2, shadow, groups_tested, sp, shade_mode, color, \
+                                                          glyph, write_hits ? 1 : 0, obj_kd)
 #define RTC_TRACE_LAUNCH(SH, T, C, A)                                                                                    \
-    trace_kernel<SH, T, C, A><<<n_ctas, T, smem, st>>>(fp, g_fast, g_exact, g_dmin, g_cone, g_sin, sphere_obj, n_spheres, \
-                                                       n_slots, objs, plane_obj, n_planes, hit_t, hit_idx, tile_counter, \
-                                                       carry_in, l0, l1, l2, shadow, groups_tested, sp, shade_mode, color, \
-                                                       glyph, write_hits ? 1 : 0, obj_kd)
+    do { if (rays == 8) RTC_TRACE_LAUNCH1(SH, T, C, A, 8); else RTC_TRACE_LAUNCH1(SH, T, C, A, 4); } while (0)
 #define RTC_TRACE_PICK(T)                                                                                                \
     do {                                                                                                                 \
         if (light) { if (cull) RTC_TRACE_LAUNCH(true, T, true, false); else RTC_TRACE_LAUNCH(true, T, false, false); }   \
@@ -726,11 +743,13 @@ cudaError_t launch_trace(cudaStream_t st, int n_ctas, const FrameParams& fp, con
         else       { if (cull) RTC_TRACE_LAUNCH(false, T, true, false); else RTC_TRACE_LAUNCH(false, T, false, false); } \
     } while (0)
     if (light && affine) return cudaErrorInvalidValue;           // shadow rays do not come from a pixel grid
+    if (rays != 8 && rays != 4) return cudaErrorInvalidValue;
     if (threads == 896) RTC_TRACE_PICK(896);
     else if (threads == 768) RTC_TRACE_PICK(768);
     else return cudaErrorInvalidValue;
 #undef RTC_TRACE_PICK
 #undef RTC_TRACE_LAUNCH
+#undef RTC_TRACE_LAUNCH1
     return cudaGetLastError();
 }
 
