@@ -666,12 +666,11 @@ size_t trace_smem_bytes(int n_slots, int threads, int rays)
 // Threads per CTA, rays per thread and sphere slots per launch for a band of `rows` rows.
 // A warp's work quantum is one tile (16 x 2*rays pixels), so T tiles take ceil(T / (CTAs * warps)) tile times, and a tile
 // time is warps / throughput(warps).  With many waves 24 and 28 warps are equally fast, but an 8-GPU band of a 4K frame
-// is 4080 tiles of 16 x 16 = 27.6 per SM: 28 warps finish it in ONE wave (profiles/r01_trace_kernel_ncu.md).  In a
-// launch of one or two waves, though, every warp is in the same phase of its tile at the same time -- ray set-up, sphere
-// loop, shading epilogue -- and set-up and epilogue (a quarter of a tile's time) overlap nothing; hence the constant
-// added to the wave count below, and hence 16 x 8 tiles (4 rays per thread; the sphere loop costs 4 % more per test) for
-// small launches: twice the waves of half the length.  More warps or rays leave less shared memory for spheres, i.e. more
-// launches over a long sphere list -- priced in per chunk.
+// is 4080 tiles of 16 x 16 = 27.6 per SM: 28 warps finish it in ONE wave (profiles/r01_trace_kernel_ncu.md).
+// 16 x 8 tiles (4 rays per thread) halve the quantum but cost 12-14 % more per test (measured, profiles/r02_band_rays.md:
+// 271 rows of a 4K frame 0.151 ms with 8 rays, 0.168 with 4; 136 rows 0.133 against 0.095), so they only pay when the
+// launch is less than about half a wave of 16 x 16 tiles -- console-sized frames, the reference's own use case.  More warps
+// or rays leave less shared memory for spheres, i.e. more launches over a long sphere list -- priced in per chunk.
 TracePlan plan_trace(uint32_t x, uint32_t rows, int n_slots, int n_ctas)
 {
     static const char* force = getenv("RTC_TRACE_THREADS_FORCE");      // experiments only
@@ -690,8 +689,8 @@ TracePlan plan_trace(uint32_t x, uint32_t rows, int n_slots, int n_ctas)
             const long long per_wave = (long long)n_ctas * w;
             const double waves = (double)((tiles + per_wave - 1) / per_wave);
             // per chunk: the sphere loop over its share of the list + a fixed ray set-up / write-back worth ~40 sphere tests
-            const double tile_time = w * rays * ((double)(n_slots > 0 ? n_slots : 1) * (rays == 4 ? 1.04 : 1.0) + 40.0 * chunks);
-            const double cost = (waves + 0.25) * tile_time;
+            const double tile_time = w * rays * ((double)(n_slots > 0 ? n_slots : 1) * (rays == 4 ? 1.14 : 1.0) + 40.0 * chunks);
+            const double cost = waves * tile_time;
             if (best_cost < 0.0 || cost < best_cost * 0.999) { best_cost = cost; best.threads = w * 32; best.max_slots = max_slots; best.rays = rays; }
         }
     }
