@@ -166,3 +166,18 @@ def test_mgpu_real_devices(ctx, rtc):
                 got.append(m.collect(copy=True))
             for k in range(len(ps)):
                 assert np.array_equal(got[k], want[k]), f"{n} GPUs, gather {g}, frame {k}"
+
+
+@pytest.mark.parametrize("backing", ["thp", "interleave"])
+def test_mgpu_alternative_host_buffers(ctx, rtc, monkeypatch, backing):
+    """RTC_MGPU_HOSTBUF: the frame buffer as registered anonymous memory (transparent huge pages / NUMA interleaving) instead
+    of cudaHostAlloc -- same bytes."""
+    monkeypatch.setenv("RTC_MGPU_HOSTBUF", backing)
+    objs = scenes.config_scene("config2_1080p_64")
+    p = rtc.camera_params(481, 270, (0, 0, -120), (0, PI32, 0), 1.0 / 480)
+    ctx.set_objects(objs)
+    want = np.array(ctx.update(p, RGB_PIXEL, dt=0.0, flags=FLAG_UPDATE_REF_LAUNCH_LIMIT))
+    with rtc.MultiGpu([0, 0, 0], rtc.GATHER_HOST) as m:
+        m.set_objects(objs)
+        for _ in range(4):
+            assert np.array_equal(m.update(p, RGB_PIXEL, 0.0, FLAG_UPDATE_REF_LAUNCH_LIMIT, copy=True), want)
