@@ -116,15 +116,10 @@ int upload_scene(rtc_ctx* c)
         c->plane_order = c->plane_obj;
     }
     const size_t n_slots = (c->sphere_obj.size() + 3) & ~(size_t)3;
-    CK(c->d_fast.ensure(n_slots > 0 ? 3 * n_slots : 12));
-    CK(c->d_cone.ensure(n_slots > 0 ? n_slots / 4 + 4 : 4));
-    CK(c->d_sin.ensure(n_slots > 0 ? n_slots / 4 + 4 : 4));
-    CK(c->d_exact.ensure(n_slots > 0 ? n_slots : 4));
-    CK(c->d_dmin.ensure(n_slots > 0 ? n_slots / 4 + 4 : 4));
     // Stage in pinned memory (two slots: the previous upload may still be in flight), then ONE async copy.
     const size_t b_objs = (n * sizeof(rtc_object) + 63) & ~(size_t)63, b_sph = (n_slots * sizeof(int32_t) + 63) & ~(size_t)63,
-                 b_pl = (c->plane_obj.size() * sizeof(int32_t) + 63) & ~(size_t)63;
-    const size_t b_all = b_objs + b_sph + b_pl + 64;
+                 b_pl = (c->plane_obj.size() * sizeof(int32_t) + 63) & ~(size_t)63, b_kd = n * sizeof(float4);
+    const size_t b_all = b_objs + b_sph + b_pl + b_kd + 64;
     // Next ring slot: stage in pinned memory, copy on the upload stream, make the frame stream wait for the copy.
     const int b = (c->scene_cur + 1) % rtc_ctx::kSceneRing;
     if (c->scene_up_pending[b]) {                               // the previous upload out of this staging slot (4 uploads ago)
@@ -148,6 +143,13 @@ int upload_scene(rtc_ctx* c)
     if (n) memcpy(h, c->objs.data(), n * sizeof(rtc_object));
     if (!c->sphere_obj.empty()) memcpy(h + b_objs, c->sphere_obj.data(), c->sphere_obj.size() * sizeof(int32_t));
     if (!c->plane_obj.empty()) memcpy(h + b_objs + b_sph, c->plane_obj.data(), c->plane_obj.size() * sizeof(int32_t));
+    // kd = colour / 255 (RayTracing.cu:144 divides per pixel; the quotient only depends on the object).  IEEE division,
+    // no contraction (-ffp-contract=off): the same float the device's __fdiv_rn would give.
+    float* kd = reinterpret_cast<float*>(h + b_objs + b_sph + b_pl);
+    for (size_t i = 0; i < n; ++i) {
+        kd[4 * i + 0] = c->objs[i].color[0] / 255.0f; kd[4 * i + 1] = c->objs[i].color[1] / 255.0f;
+        kd[4 * i + 2] = c->objs[i].color[2] / 255.0f; kd[4 * i + 3] = 0.0f;
+    }
     if (c->scene_rd_recorded[b]) CK(cudaStreamWaitEvent(c->upload_stream, c->ev_scene_rd[b], 0));   // frames still reading this device slot
     CK(cudaMemcpyAsync(c->d_scene[b].p, h, b_all - 64, cudaMemcpyHostToDevice, c->upload_stream));
     CK(cudaEventRecord(c->ev_scene_up[b], c->upload_stream));
@@ -157,6 +159,7 @@ int upload_scene(rtc_ctx* c)
     c->d_objs.p = reinterpret_cast<rtc_object*>(c->d_scene[b].p);
     c->d_sphere_obj.p = reinterpret_cast<int32_t*>(c->d_scene[b].p + b_objs);
     c->d_plane_obj.p = reinterpret_cast<int32_t*>(c->d_scene[b].p + b_objs + b_sph);
+    c->d_kd.p = reinterpret_cast<float4*>(c->d_scene[b].p + b_objs + b_sph + b_pl);
     c->scene_dirty = false;
     return RTC_OK;
 }
@@ -240,8 +243,11 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
     c->last_launches = 0;
     if (record_events) CK(cudaEventRecord(c->ev[0], c->stream));
     const bool cull = (flags & RTC_FLAG_CULL) != 0;
-    unsigned long long* stats = reinterpret_cast<unsigned long long*>(c->d_counters.p + rtc::kStatsCounter);   // zeroed by the hoist
-    CK(c->d_kd.ensure(c->objs.size() + 4));
+    // test counts of this frame: parity p; every launch of the frame zeroes parity p ^ 1 for the next one (so the parity
+    // only moves when something is launched)
+    if (n_px > 0) c->stats_parity ^= 1u;
+    unsigned long long* stats = c->d_counters.p + rtc::kStatsCounter + 2 * c->stats_parity;
+    unsigned long long* stats_zero = c->d_counters.p + rtc::kStatsCounter + 2 * (c->stats_parity ^ 1u);
     // The screen-affine packed filter (rtc_trace.cu) assumes what every camera gives: a near-orthonormal 3x3 inverse view
     // matrix (its error bound is relative to |w| = |col2 + vx col0 + vy col1|; cancellation between skewed columns would
     // void it).  Anything else -- the C-ABI accepts arbitrary matrices -- runs the dot-product form of the filter.
@@ -252,11 +258,6 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
             const double dot = (double)fp0.m[a] * fp0.m[b] + (double)fp0.m[4 + a] * fp0.m[4 + b] + (double)fp0.m[8 + a] * fp0.m[8 + b];
             if (!(fabs(dot - (a == b ? 1.0 : 0.0)) < 1.0e-3)) affine = false;
         }
-    CK(rtc::launch_hoist(c->stream, c->d_objs.p, c->d_sphere_obj.p, n_spheres, n_slots, p->cam_pos, c->d_fast.p,
-                         c->d_exact.p, c->d_dmin.p, c->d_cone.p, c->d_sin.p, c->d_counters.p, rtc::kNumCounters, c->d_kd.p,
-                         (int)c->objs.size(), affine ? fp0.m : nullptr));
-
-    c->last_launches++;
     const bool shadows = (flags & RTC_FLAG_SHADOWS) != 0 && mode != RTC_SDL && mode != RTC_RGB_NORMALS;
     // Without shadow rays the ray kernel shades + quantises in its tile epilogue (one launch, no hit-record round trip);
     // hit records are then written only on request.  With shadow rays the records feed the light-origin pass and the
@@ -264,16 +265,6 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
     const bool fused = !shadows && mode != RTC_SDL;
     const int shade_mode = (mode == RTC_RGB_NORMALS && (flags & RTC_FLAG_NORMALS_SATURATE)) ? rtc::kModeNormalsSaturate : mode;
     const bool keep_hits = (flags & RTC_FLAG_KEEP_HITS) != 0 || shadows;
-    if (shadows) {
-        CK(c->d_fast_l.ensure(n_slots > 0 ? 3 * (size_t)n_slots : 12));
-        CK(c->d_exact_l.ensure(n_slots > 0 ? n_slots : 4));
-        CK(c->d_dmin_l.ensure(n_slots > 0 ? n_slots / 4 + 4 : 4));
-        CK(c->d_cone_l.ensure(n_slots > 0 ? n_slots / 4 + 4 : 4));
-        CK(c->d_sin_l.ensure(n_slots > 0 ? n_slots / 4 + 4 : 4));
-        CK(rtc::launch_hoist(c->stream, c->d_objs.p, c->d_sphere_obj.p, n_spheres, n_slots, c->shade.light, c->d_fast_l.p,
-                             c->d_exact_l.p, c->d_dmin_l.p, c->d_cone_l.p, c->d_sin_l.p, c->d_counters.p, 0, nullptr, 0, nullptr));
-        c->last_launches++;
-    }
     if (record_events) CK(cudaEventRecord(c->ev[1], c->stream));
     c->hits_valid = false;
     if (n_px > 0) {
@@ -281,6 +272,7 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
         const rtc::TracePlan plan = rtc::plan_trace(p->x, row1 - row0, n_slots, c->sm_count);
         const int n_chunks = n_slots == 0 ? 1 : (n_slots + plan.max_slots - 1) / plan.max_slots;
         if (n_chunks > rtc::kMaxChunks) return fail(RTC_ERR_CAPACITY, "too many spheres (%d)", n_spheres);
+        const unsigned long long tickets = rtc::trace_tickets(p->x, row1 - row0, c->sm_count, plan.threads, plan.rays);
         if (keep_hits || n_chunks > 1) {
             CK(c->d_hit_t.ensure(n_px));
             CK(c->d_hit_idx.ensure(n_px));
@@ -290,11 +282,12 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
             const int slots = n_slots - s0 < plan.max_slots ? n_slots - s0 : plan.max_slots;
             const int sph = n_spheres - s0 < slots ? n_spheres - s0 : slots;
             const bool last = ch == n_chunks - 1;
-            CK(rtc::launch_trace(c->stream, c->sm_count, fp, c->d_fast.p + 3 * (size_t)s0, c->d_exact.p + s0, c->d_dmin.p + s0 / 4,
-                                 c->d_cone.p + s0 / 4, c->d_sin.p + s0 / 4, c->d_sphere_obj.p + s0,
+            CK(rtc::launch_trace(c->stream, c->sm_count, fp, c->d_sphere_obj.p + s0,
                                  sph, slots, c->d_objs.p, c->d_plane_obj.p, last ? n_planes : 0, c->d_hit_t.p,
-                                 c->d_hit_idx.p, c->d_counters.p + ch, ch > 0 ? 1 : 0, nullptr, nullptr, plan.threads, cull, stats,
-                                 c->shade, fused && last ? shade_mode : -1, d_color, d_glyph, !last || keep_hits, c->d_kd.p, affine, plan.rays));
+                                 c->d_hit_idx.p, c->d_counters.p + ch, c->ticket_base[ch], ch > 0 ? 1 : 0, nullptr, nullptr, plan.threads,
+                                 cull, stats, stats_zero, c->shade, fused && last ? shade_mode : -1, d_color, d_glyph,
+                                 !last || keep_hits, c->d_kd.p, affine, plan.rays));
+            c->ticket_base[ch] += tickets;
             c->last_launches++;
         }
         c->hits_valid = keep_hits;
@@ -305,11 +298,12 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
                 const int slots = n_slots - s0 < plan.max_slots ? n_slots - s0 : plan.max_slots;
                 const int sph = n_spheres - s0 < slots ? n_spheres - s0 : slots;
                 const bool last = ch == n_chunks - 1;
-                CK(rtc::launch_trace(c->stream, c->sm_count, fp, c->d_fast_l.p + 3 * (size_t)s0, c->d_exact_l.p + s0,
-                                     c->d_dmin_l.p + s0 / 4, c->d_cone_l.p + s0 / 4, c->d_sin_l.p + s0 / 4, c->d_sphere_obj.p + s0, sph, slots,
+                CK(rtc::launch_trace(c->stream, c->sm_count, fp, c->d_sphere_obj.p + s0, sph, slots,
                                      c->d_objs.p, c->d_plane_obj.p, last ? n_planes : 0,
-                                     c->d_hit_t.p, c->d_hit_idx.p, c->d_counters.p + 32 + ch, ch > 0 ? 1 : 0, c->shade.light,
-                                     c->d_shadow.p, plan.threads, cull, stats + 1, c->shade, -1, nullptr, nullptr, false, nullptr, false, plan.rays));
+                                     c->d_hit_t.p, c->d_hit_idx.p, c->d_counters.p + rtc::kMaxChunks + ch, c->ticket_base[rtc::kMaxChunks + ch],
+                                     ch > 0 ? 1 : 0, c->shade.light, c->d_shadow.p, plan.threads, cull, stats + 1, stats_zero, c->shade, -1,
+                                     nullptr, nullptr, false, nullptr, false, plan.rays));
+                c->ticket_base[rtc::kMaxChunks + ch] += tickets;
                 c->last_launches++;
             }
         }
@@ -380,7 +374,7 @@ int rtc_create(rtc_ctx** out, int device)
     CKC(rtc::configure_trace());
     CKC(rtc::configure_encode());
     CKC(c->d_counters.ensure(rtc::kNumCounters));
-    CKC(cudaMemset(c->d_counters.p, 0, rtc::kNumCounters * sizeof(unsigned int)));
+    CKC(cudaMemset(c->d_counters.p, 0, rtc::kNumCounters * sizeof(unsigned long long)));
     CKC(c->d_total.ensure(2));
     CKC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (auto& ev : c->ev_total) CKC(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -401,9 +395,7 @@ void rtc_destroy(rtc_ctx* c)
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     if (c->upload_stream) { cudaStreamSynchronize(c->upload_stream); cudaStreamDestroy(c->upload_stream); }
     for (auto& b : c->d_scene) b.release();
-    c->d_fast.release(); c->d_exact.release();
-    c->d_fast_l.release(); c->d_exact_l.release(); c->d_shadow.release(); c->d_kd.release(); c->d_dmin.release(); c->d_dmin_l.release();
-    c->d_cone.release(); c->d_cone_l.release(); c->d_sin.release(); c->d_sin_l.release();
+    c->d_shadow.release();
     c->d_hit_t.release(); c->d_hit_idx.release(); c->d_color.release(); c->d_glyph.release(); c->d_out[0].release(); c->d_out[1].release();
     c->d_desc.release(); c->d_counters.release(); c->d_total.release(); c->d_sink.release();
     c->h_total.release(); c->h_out[0].release(); c->h_out[1].release(); for (auto& b : c->h_scene) b.release();
@@ -707,7 +699,7 @@ int rtc_last_timings(rtc_ctx* c, rtc_timings* out)
     out->launches = c->last_launches;
     // packed ray-sphere tests the last frame executed: warps x groups x (4 spheres x 256 rays), both passes
     unsigned long long groups[2] = {0ull, 0ull};
-    CK(cudaMemcpyAsync(groups, c->d_counters.p + rtc::kStatsCounter, sizeof groups, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(groups, c->d_counters.p + rtc::kStatsCounter + 2 * c->stats_parity, sizeof groups, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     out->sphere_tests = (groups[0] + groups[1]) * 4ull * 32ull;        // the kernel counts groups x rays per thread
     return RTC_OK;

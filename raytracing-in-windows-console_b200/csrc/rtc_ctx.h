@@ -89,15 +89,8 @@ struct rtc_ctx {
     bool scene_up_pending[kSceneRing] = {}, scene_rd_recorded[kSceneRing] = {};
     struct View { rtc_object* p = nullptr; } d_objs;
     struct ViewI { int32_t* p = nullptr; } d_sphere_obj, d_plane_obj;
-    rtc::DevBuf<float> d_fast;      // 12 B per sphere slot (slots padded to a multiple of 4)
-    rtc::DevBuf<float4> d_exact;
-    rtc::DevBuf<float> d_dmin, d_dmin_l;   // per group of 4 spheres: lower bound of any hit distance (camera / light origin)
-    rtc::DevBuf<float4> d_cone, d_cone_l;  // per group: bounding cone seen from the origin (axis, cos half-angle) ...
-    rtc::DevBuf<float> d_sin, d_sin_l;     // ... and the sine of its half-angle (RTC_FLAG_CULL)
-    rtc::DevBuf<float> d_fast_l;    // the same hoist with the light as origin (shadow-ray extension)
-    rtc::DevBuf<float4> d_exact_l;
+    struct ViewK { float4* p = nullptr; } d_kd;     // per object: colour / 255 (RayTracing.cu:144), computed on the host at upload
     rtc::DevBuf<uint8_t> d_shadow;  // 1 byte per pixel: occluded
-    rtc::DevBuf<float4> d_kd;       // per object: colour / 255 (hoisted out of the per-pixel shading)
 
     // frame buffers
     rtc::DevBuf<float> d_hit_t;
@@ -106,8 +99,9 @@ struct rtc_ctx {
     rtc::DevBuf<char> d_out[2];                  // two frame slots: the stream of frame k is copied out while k+1 is encoded
     rtc::DevBuf<unsigned char> d_desc;           // encoder scratch: per-tile counts, group accumulators (two parities)
     uint32_t enc_parity = 0;
-    rtc::DevBuf<unsigned int> d_counters;        // zeroed by the hoist every frame: [0..27] tile tickets of the primary pass (one per
-                                            // sphere chunk), [32..59] of the shadow pass, [60..63] two 64-bit counts of groups tested
+    rtc::DevBuf<unsigned long long> d_counters;  // rtc_kernels.h: tile tickets (never reset) + two parities of test counts
+    unsigned long long ticket_base[2 * rtc::kMaxChunks] = {};   // tickets each counter has handed out so far
+    uint32_t stats_parity = 0;                   // parity of the last frame's test counts
     rtc::DevBuf<unsigned long long> d_total;     // [2]
     rtc::DevBuf<float> d_sink;
     rtc::PinBuf<unsigned long long> h_total;     // [2]

@@ -13,26 +13,26 @@ struct ShadeParams;
 // The persistent ray-kernel CTA (one per SM) exists with 24 and with 28 warps; plan_trace picks per launch.
 struct TracePlan { int threads; int max_slots; int rays; };   // threads per CTA; sphere slots resident in shared memory per launch; rays per thread (8 or 4)
 TracePlan plan_trace(uint32_t x, uint32_t rows, int n_slots, int n_ctas);
-constexpr int kNumCounters = 64;           // per-frame device counters zeroed by the hoist kernel
-constexpr int kMaxChunks = 28;             // sphere-list chunks per pass (one tile ticket each): 69k spheres at 24 warps
-constexpr int kStatsCounter = 60;          // [60..63]: two 64-bit counts of sphere groups tested (primary, shadow pass)
+constexpr int kMaxChunks = 28;             // sphere-list chunks per pass (one ticket counter each): 69k spheres at 24 warps
+// Device counters of a context, all 64-bit, zeroed once at creation and never reset: [0 .. kMaxChunks) tile tickets of the
+// primary pass (one per sphere chunk), [kMaxChunks .. 2 kMaxChunks) of the shadow pass -- a launch draws its tickets above
+// the base the host keeps (trace_tickets) --, then two frame parities x (primary, shadow) counts of sphere groups tested.
+constexpr int kStatsCounter = 2 * kMaxChunks;
+constexpr int kNumCounters = kStatsCounter + 4;
 
-// kernel 0 / 1 (rtc_trace.cu)
+// kernel 1 (rtc_trace.cu): per-frame scene hoist (every CTA, into its shared memory) + ray generation + nearest hit
+// (+ shade/quantise epilogue)
 cudaError_t configure_trace();
 size_t trace_smem_bytes(int n_slots, int threads, int rays);
-cudaError_t launch_hoist(cudaStream_t st, const rtc_object* objs, const int32_t* sphere_obj, int n_spheres,
-                         int n_slots, const float cam[3], float* sph_fast, float4* sph_exact, float* grp_dmin,
-                         float4* grp_cone, float* grp_sin, unsigned int* counters, int n_counters,
-                         float4* obj_kd /* NULL: leave it */, int n_objs,
-                         const float* affine_m /* NULL: dot-product layout; else FrameParams::m: screen-affine layout */);
-cudaError_t launch_trace(cudaStream_t st, int n_ctas, const FrameParams& fp, const float* g_fast, const float4* g_exact,
-                         const float* g_dmin, const float4* g_cone, const float* g_sin, const int32_t* sphere_obj, int n_spheres,
+unsigned long long trace_tickets(uint32_t x, uint32_t rows, int n_ctas, int threads, int rays);
+cudaError_t launch_trace(cudaStream_t st, int n_ctas, const FrameParams& fp, const int32_t* sphere_obj, int n_spheres,
                          int n_slots, const rtc_object* objs, const int32_t* plane_obj, int n_planes, float* hit_t,
-                         int32_t* hit_idx, unsigned int* tile_counter, int carry_in, const float* light /* NULL: primary rays */,
-                         uint8_t* shadow, int threads, bool cull, unsigned long long* groups_tested,
+                         int32_t* hit_idx, unsigned long long* tile_counter, unsigned long long ticket_base, int carry_in,
+                         const float* light /* NULL: primary rays */, uint8_t* shadow, int threads, bool cull,
+                         unsigned long long* groups_tested, unsigned long long* stats_zero,
                          const ShadeParams& sp, int shade_mode /* >= 0: shade + quantise in the tile epilogue; -1: no */,
                          uint8_t* color, uint8_t* glyph, bool write_hits, const float4* obj_kd /* per object colour / 255 */,
-                         bool affine /* g_fast is in the screen-affine layout (primary rays only) */, int rays /* per thread: 8 or 4 */);
+                         bool affine /* screen-affine packed filter (primary rays only) */, int rays /* per thread: 8 or 4 */);
 
 // kernel 2 (rtc_shade.cu): stand-alone shade + quantise, used only after a shadow pass
 cudaError_t launch_shade(cudaStream_t st, const FrameParams& fp, const ShadeParams& sp, int mode,

@@ -50,114 +50,6 @@ struct HoistBasis {
     float c0[3], c1[3], c2[3];
 };
 
-// ---- kernel 0: hoist --------------------------------------------------------------------
-// One thread per sphere slot (slots are padded to a multiple of 4).
-//   sph_fast : per GROUP of 4 spheres 12 floats: gx[4], gy[4], gz[4] with g = oc * 2^64/sqrt(c')
-//              (three LDS.128 feed two packed sphere pairs)
-//   sph_exact: per sphere float4 (ocx, ocy, ocz, c), exact.
-// Slots past n_spheres are never-hit sentinels (g = 0).  c' <= 0 (camera inside / on the
-// sphere) or non-finite geometry => g = inf: always a candidate, the exact path decides.
-__global__ void __launch_bounds__(256)
-hoist_kernel(const rtc_object* __restrict__ objs, const int32_t* __restrict__ sphere_obj, int n_spheres,
-             int n_slots, float camx, float camy, float camz, float* __restrict__ sph_fast,
-             float4* __restrict__ sph_exact, float* __restrict__ grp_dmin, float4* __restrict__ grp_cone,
-             float* __restrict__ grp_sin, unsigned int* __restrict__ counters, int n_counters,
-             float4* __restrict__ obj_kd, int n_objs, const HoistBasis hb)
-{
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < n_counters) counters[j] = 0u;     // tile tickets for this frame
-    // per OBJECT: kd = colour / 255 (RayTracing.cu:144 divides per pixel; the quotient only depends on the object)
-    if (obj_kd != nullptr && j < n_objs)
-        obj_kd[j] = make_float4(dvd(objs[j].color[0], 255.0f), dvd(objs[j].color[1], 255.0f), dvd(objs[j].color[2], 255.0f), 0.0f);
-    // (no early return: the group minimum below is a warp shuffle; n_slots is a multiple of 4, blockDim of 32)
-    float ocx = 0.f, ocy = 0.f, ocz = 0.f, c = 1.f, gx = 0.f, gy = 0.f, gz = 0.f;
-    float dmin = 3.0e38f;                     // lower bound of any reference hit distance on this sphere
-    float wx = 0.f, wy = 0.f, wz = 0.f, wr = 0.f, wn = 0.f;   // world centre, radius, 1 if this slot holds a sphere
-    if (j < n_spheres) {
-        const rtc_object& s = objs[sphere_obj[j]];
-        wx = s.center[0]; wy = s.center[1]; wz = s.center[2]; wr = fabsf(s.radius); wn = 1.0f;
-        ocx = sub(camx, s.center[0]);                                   // Sphere.cu:34
-        ocy = sub(camy, s.center[1]);
-        ocz = sub(camz, s.center[2]);
-        const float oc2 = vdot(v3(ocx, ocy, ocz), v3(ocx, ocy, ocz));
-        c = sub(oc2, mul(s.radius, s.radius));                          // Sphere.cu:37
-        const float cd = fmaf(-RTC_FILTER_EPS, oc2, c);                 // deflated c'
-        const float inf = __int_as_float(0x7f800000);
-        if (cd > 0.0f && cd < 3.0e38f) {
-            if (hb.affine) {
-                // screen-affine filter: (A, B, C) = g . (col0, col1, col2) of the inverse view matrix, g = oc 2^64 / sqrt(c'),
-                // in binary64 and rounded once (stored where the dot-product form keeps gx, gy, gz)
-                const double gs = 18446744073709551616.0 / sqrt((double)cd);
-                const double dx = (double)ocx * gs, dy = (double)ocy * gs, dz = (double)ocz * gs;
-                gx = (float)(dx * (double)hb.c0[0] + dy * (double)hb.c0[1] + dz * (double)hb.c0[2]);
-                gy = (float)(dx * (double)hb.c1[0] + dy * (double)hb.c1[1] + dz * (double)hb.c1[2]);
-                gz = (float)(dx * (double)hb.c2[0] + dy * (double)hb.c2[1] + dz * (double)hb.c2[2]);
-            } else {
-                const float g = RTC_TWO64 / sqrtf(cd);
-                gx = ocx * g; gy = ocy * g; gz = ocz * g;
-            }
-            // Lower bound of the reference's ROUNDED hit distance over every ray: the minimum over s1 of exact_group's
-            // per-candidate bound t_lb(s1) (same discriminant slack: the rounding error of b*b - 4ac, ~23u|oc|^2, is
-            // amplified by the sqrt, so near-tangent hits of small or distant spheres come out up to ~3e-3|oc| NEARER
-            // than the geometric |oc| - r).  With p = -s1 and K = 3e-6(|oc|^2 + |c|) - c < 0 (implied by c' > 0),
-            // t_lb(p) = p - sqrt(p^2 + K)(1 + 1e-6) - 2e-6(p + |oc|) decreases in p, so its minimum sits at the largest
-            // p a unit direction (to 1e-6) allows, p = |oc|(1 + 1e-6).  Evaluated in binary64, then rounded down.
-            const double L = sqrt((double)oc2) * 1.000001;
-            const double K = 3.0e-6 * ((double)oc2 + fabs((double)c)) - (double)c;
-            const double q = fmax(L * L + K, 0.0);
-            const double lb = (L - sqrt(q) * 1.000001) - 2.0e-6 * (2.0 * L);
-            dmin = fmaxf((float)(lb * (lb >= 0.0 ? 0.999999 : 1.000001)) - 1.0e-30f, 0.0f);
-#ifdef RTC_TEST_R01_GROUP_BOUND   // the round-1 bound (geometric |oc| - r): kept only to show that the regression test bites
-            dmin = fmaxf((sqrtf(oc2) - fabsf(s.radius)) - 1.0e-5f * (sqrtf(oc2) + fabsf(s.radius)), 0.0f);
-#endif
-        } else {
-            gx = gy = gz = inf;
-            dmin = 0.0f;
-        }
-    }
-    dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, 1));
-    dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, 2));
-    // Bounding sphere of the group of 4 (centre = mean of the centres, radius = max(|c_i - centre| + r_i)) as a cone
-    // seen from the ray origin: unit axis u, sin and cos of its half-angle, both rounded towards "wider".
-    // No sphere in the group: never kept.  Origin inside the bounding sphere or odd numbers: always kept.
-    float sx = wx, sy = wy, sz = wz, sn = wn;
-#pragma unroll
-    for (int o = 1; o <= 2; o <<= 1) {
-        sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o);
-        sz += __shfl_xor_sync(0xffffffffu, sz, o); sn += __shfl_xor_sync(0xffffffffu, sn, o);
-    }
-    const float inv_n = sn > 0.0f ? 1.0f / sn : 0.0f;
-    const float mx = sx * inv_n, my = sy * inv_n, mz = sz * inv_n;
-    float R = wn > 0.0f ? sqrtf((wx - mx) * (wx - mx) + (wy - my) * (wy - my) + (wz - mz) * (wz - mz)) + wr : 0.0f;
-    R = fmaxf(R, __shfl_xor_sync(0xffffffffu, R, 1));
-    R = fmaxf(R, __shfl_xor_sync(0xffffffffu, R, 2));
-    if (j >= n_slots) return;
-    if ((j & 3) == 0) {
-        float4 cone = make_float4(0.f, 0.f, 0.f, 3.0f);          // empty group: threshold 3 cos(theta) > 1 >= any dot
-        float sn_a = 0.0f;
-        if (sn > 0.0f) {
-            const float vx = mx - camx, vy = my - camy, vz = mz - camz;
-            const float L = sqrtf(vx * vx + vy * vy + vz * vz);
-            const float Ri = R * 1.00002f + 1.0e-5f * (L + R);   // inflated: covers the rounding of everything above
-            if (L > Ri && L < 3.0e37f && Ri == Ri) {
-                const float sa = fminf(Ri / L * 1.000001f + 1.0e-7f, 1.0f);
-                const float ca = sqrtf(fmaxf(1.0f - sa * sa, 0.0f)) * 0.999999f;
-                cone = make_float4(vx / L, vy / L, vz / L, ca);
-                sn_a = sa;
-            } else {
-                cone = make_float4(0.f, 0.f, 0.f, -3.0f);        // always kept: threshold < 0 <= dot = 0
-            }
-        }
-        grp_cone[j >> 2] = cone;
-        grp_sin[j >> 2] = sn_a;
-    }
-    float* base = sph_fast + 12 * (j >> 2);
-    const int k = j & 3;
-    base[k] = gx; base[4 + k] = gy; base[8 + k] = gz;
-    sph_exact[j] = make_float4(ocx, ocy, ocz, c);
-    if (k == 0) grp_dmin[j >> 2] = dmin;
-}
-
 // ---- kernel 1: trace --------------------------------------------------------------------
 // Rays per thread are a template parameter (kRays = 8 or 4): a thread owns one column and kRays rows (every other row) of
 // its warp's 16 x 2*kRays tile.  8 is the efficient shape (the per-column operand F of the screen-affine filter is
@@ -228,6 +120,113 @@ __device__ __forceinline__ float4 lds128(uint32_t addr)
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
+}
+
+// ---- per-frame scene hoist, done by every CTA of the ray kernel for its own shared-memory copy -----------------------
+// (Round 1 and the first half of round 2 ran this as a launch of its own that wrote global arrays every CTA then staged;
+// a 1000-sphere list is one slot per thread of a CTA, so recomputing it 148 times costs nothing and saves a launch, its
+// gap, and a global round trip per frame -- 5 % of an 8-GPU band, 20 % of a console-sized frame.)
+// Per sphere slot j (slots are padded to a multiple of 4; a warp's 4-lane groups see 4 consecutive slots):
+//   fast : per GROUP of 4 spheres 12 floats: gx[4], gy[4], gz[4] with g = oc * 2^64/sqrt(c') -- or, screen-affine form,
+//          (A, B, C)[4] = g . (col0, col1, col2) -- (three LDS.128 feed two packed sphere pairs)
+//   exact: per sphere float4 (ocx, ocy, ocz, c), exact.
+// Slots past n_spheres are never-hit sentinels (g = 0).  c' <= 0 (origin inside / on the sphere) or non-finite geometry
+// => g = inf: always a candidate, the exact path decides.
+__device__ __noinline__ void hoist_into_smem(const Smem sm, const rtc_object* __restrict__ objs, const int32_t* __restrict__ sphere_obj,
+                                             int n_spheres, int n_slots, float camx, float camy, float camz, const HoistBasis hb,
+                                             bool want_cone, int tid, int n_threads)
+{
+    for (int j0 = 0; j0 < n_slots; j0 += n_threads) {          // n_threads is a multiple of 32: warp-uniform trip count
+    const int j = j0 + tid;
+    // (no early return: the group minimum below is a warp shuffle; n_slots is a multiple of 4, blockDim of 32)
+    float ocx = 0.f, ocy = 0.f, ocz = 0.f, c = 1.f, gx = 0.f, gy = 0.f, gz = 0.f;
+    float dmin = 3.0e38f;                     // lower bound of any reference hit distance on this sphere
+    float wx = 0.f, wy = 0.f, wz = 0.f, wr = 0.f, wn = 0.f;   // world centre, radius, 1 if this slot holds a sphere
+    if (j < n_spheres) {
+        const rtc_object& s = objs[sphere_obj[j]];
+        wx = s.center[0]; wy = s.center[1]; wz = s.center[2]; wr = fabsf(s.radius); wn = 1.0f;
+        ocx = sub(camx, s.center[0]);                                   // Sphere.cu:34
+        ocy = sub(camy, s.center[1]);
+        ocz = sub(camz, s.center[2]);
+        const float oc2 = vdot(v3(ocx, ocy, ocz), v3(ocx, ocy, ocz));
+        c = sub(oc2, mul(s.radius, s.radius));                          // Sphere.cu:37
+        const float cd = fmaf(-RTC_FILTER_EPS, oc2, c);                 // deflated c'
+        const float inf = __int_as_float(0x7f800000);
+        if (cd > 0.0f && cd < 3.0e38f) {
+            if (hb.affine) {
+                // screen-affine filter: (A, B, C) = g . (col0, col1, col2) of the inverse view matrix, g = oc 2^64 / sqrt(c'),
+                // in binary64 and rounded once (stored where the dot-product form keeps gx, gy, gz)
+                const double gs = 18446744073709551616.0 / sqrt((double)cd);
+                const double dx = (double)ocx * gs, dy = (double)ocy * gs, dz = (double)ocz * gs;
+                gx = (float)(dx * (double)hb.c0[0] + dy * (double)hb.c0[1] + dz * (double)hb.c0[2]);
+                gy = (float)(dx * (double)hb.c1[0] + dy * (double)hb.c1[1] + dz * (double)hb.c1[2]);
+                gz = (float)(dx * (double)hb.c2[0] + dy * (double)hb.c2[1] + dz * (double)hb.c2[2]);
+            } else {
+                const float g = RTC_TWO64 / sqrtf(cd);
+                gx = ocx * g; gy = ocy * g; gz = ocz * g;
+            }
+            // Lower bound of the reference's ROUNDED hit distance over every ray: the minimum over s1 of exact_group's
+            // per-candidate bound t_lb(s1) (same discriminant slack: the rounding error of b*b - 4ac, ~23u|oc|^2, is
+            // amplified by the sqrt, so near-tangent hits of small or distant spheres come out up to ~3e-3|oc| NEARER
+            // than the geometric |oc| - r).  With p = -s1 and K = 3e-6(|oc|^2 + |c|) - c < 0 (implied by c' > 0),
+            // t_lb(p) = p - sqrt(p^2 + K)(1 + 1e-6) - 2e-6(p + |oc|) decreases in p, so its minimum sits at the largest
+            // p a unit direction (to 1e-6) allows, p = |oc|(1 + 1e-6).  Evaluated in binary64, then rounded down.
+            const double L = sqrt((double)oc2) * 1.000001;
+            const double K = 3.0e-6 * ((double)oc2 + fabs((double)c)) - (double)c;
+            const double q = fmax(L * L + K, 0.0);
+            const double lb = (L - sqrt(q) * 1.000001) - 2.0e-6 * (2.0 * L);
+            dmin = fmaxf((float)(lb * (lb >= 0.0 ? 0.999999 : 1.000001)) - 1.0e-30f, 0.0f);
+#ifdef RTC_TEST_R01_GROUP_BOUND   // the round-1 bound (geometric |oc| - r): kept only to show that the regression test bites
+            dmin = fmaxf((sqrtf(oc2) - fabsf(s.radius)) - 1.0e-5f * (sqrtf(oc2) + fabsf(s.radius)), 0.0f);
+#endif
+        } else {
+            gx = gy = gz = inf;
+            dmin = 0.0f;
+        }
+    }
+    dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, 1));
+    dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, 2));
+    // Bounding sphere of the group of 4 (centre = mean of the centres, radius = max(|c_i - centre| + r_i)) as a cone
+    // seen from the ray origin: unit axis u, sin and cos of its half-angle, both rounded towards "wider".
+    // No sphere in the group: never kept.  Origin inside the bounding sphere or odd numbers: always kept.
+    float sx = wx, sy = wy, sz = wz, sn = wn;
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        sz += __shfl_xor_sync(0xffffffffu, sz, o); sn += __shfl_xor_sync(0xffffffffu, sn, o);
+    }
+    const float inv_n = sn > 0.0f ? 1.0f / sn : 0.0f;
+    const float mx = sx * inv_n, my = sy * inv_n, mz = sz * inv_n;
+    float R = wn > 0.0f ? sqrtf((wx - mx) * (wx - mx) + (wy - my) * (wy - my) + (wz - mz) * (wz - mz)) + wr : 0.0f;
+    R = fmaxf(R, __shfl_xor_sync(0xffffffffu, R, 1));
+    R = fmaxf(R, __shfl_xor_sync(0xffffffffu, R, 2));
+    if (j < n_slots) {
+    if (want_cone && (j & 3) == 0) {
+        float4 cone = make_float4(0.f, 0.f, 0.f, 3.0f);          // empty group: threshold 3 cos(theta) > 1 >= any dot
+        float sn_a = 0.0f;
+        if (sn > 0.0f) {
+            const float vx = mx - camx, vy = my - camy, vz = mz - camz;
+            const float L = sqrtf(vx * vx + vy * vy + vz * vz);
+            const float Ri = R * 1.00002f + 1.0e-5f * (L + R);   // inflated: covers the rounding of everything above
+            if (L > Ri && L < 3.0e37f && Ri == Ri) {
+                const float sa = fminf(Ri / L * 1.000001f + 1.0e-7f, 1.0f);
+                const float ca = sqrtf(fmaxf(1.0f - sa * sa, 0.0f)) * 0.999999f;
+                cone = make_float4(vx / L, vy / L, vz / L, ca);
+                sn_a = sa;
+            } else {
+                cone = make_float4(0.f, 0.f, 0.f, -3.0f);        // always kept: threshold < 0 <= dot = 0
+            }
+        }
+        sm.gcone[j >> 2] = cone;
+        sm.gsin[j >> 2] = sn_a;
+    }
+    float* base = reinterpret_cast<float*>(sm.fast) + 12 * (j >> 2);
+    const int k = j & 3;
+    base[k] = gx; base[4 + k] = gy; base[8 + k] = gz;
+    sm.exact[j] = make_float4(ocx, ocy, ocz, c);
+    if (k == 0) sm.gdmin[j >> 2] = dmin;
+    }
+    }
 }
 
 // The rare path: exact re-evaluation of the candidates of one loop iteration (4 spheres x 8 rays).
@@ -378,13 +377,14 @@ __device__ __forceinline__ void test_group(const Smem& s, uint32_t fa, int g, co
 // AFFINE = true: the screen-affine packed filter (see test_group); primary rays only.
 template <bool SHADOW, int kThreads, bool CULL, bool AFFINE, int kRays>
 __global__ void __launch_bounds__(kThreads, 1)
-trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float4* __restrict__ g_exact,
-             const float* __restrict__ g_dmin, const float4* __restrict__ g_cone, const float* __restrict__ g_sin,
+trace_kernel(const FrameParams fp, const HoistBasis hb,
              const int32_t* __restrict__ sphere_obj, int n_spheres, int n_slots,
              const rtc_object* __restrict__ objs, const int32_t* __restrict__ plane_obj, int n_planes,
-             float* __restrict__ hit_t, int32_t* __restrict__ hit_idx, unsigned int* __restrict__ tile_counter,
+             float* __restrict__ hit_t, int32_t* __restrict__ hit_idx, unsigned long long* __restrict__ tile_counter,
+             unsigned long long ticket_base /* tickets this counter has handed out before this launch (never reset) */,
              int carry_in /* 1: continue from hit_t/hit_idx (sphere list chunking) */,
              float lx, float ly, float lz, uint8_t* __restrict__ shadow, unsigned long long* __restrict__ groups_tested,
+             unsigned long long* __restrict__ stats_zero /* the other frame parity's two counts: zeroed here for the next frame */,
              const ShadeParams sp, int shade_mode /* >= 0: shade + quantise into color / glyph in the tile epilogue */,
              uint8_t* __restrict__ color, uint8_t* __restrict__ glyph, int write_hits, const float4* __restrict__ obj_kd)
 {
@@ -400,12 +400,10 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
     }
     unsigned int my_groups = 0;                                  // groups of 4 spheres this warp ran the packed test on
 
-    // Stage the hoisted sphere list once per CTA (persistent kernel).
-    for (int i = tid; i < n_slots; i += kThreads) s.exact[i] = g_exact[i];
-    for (int i = tid; i < (n_slots >> 2) * 3; i += kThreads) s.fast[i] = reinterpret_cast<const float4*>(g_fast)[i];
-    for (int i = tid; i < (n_slots >> 2); i += kThreads) s.gdmin[i] = g_dmin[i];
-    if (CULL)
-        for (int i = tid; i < (n_slots >> 2); i += kThreads) { s.gcone[i] = g_cone[i]; s.gsin[i] = g_sin[i]; }
+    if (blockIdx.x == 0 && tid == 0 && stats_zero != nullptr) { stats_zero[0] = 0ull; stats_zero[1] = 0ull; }
+    // Hoist this launch's sphere slots into shared memory, once per CTA (persistent kernel).
+    hoist_into_smem(s, objs, sphere_obj, n_spheres, n_slots, SHADOW ? lx : fp.cam[0], SHADOW ? ly : fp.cam[1], SHADOW ? lz : fp.cam[2],
+                    hb, CULL, tid, kThreads);
     __syncthreads();
 
     const uint32_t W = fp.x - 1u;
@@ -419,10 +417,11 @@ trace_kernel(const FrameParams fp, const float* __restrict__ g_fast, const float
     const uint32_t fast_base = (uint32_t)__cvta_generic_to_shared(s.fast);
 
     for (;;) {
-        uint32_t tile = 0;
-        if (lane == 0) tile = atomicAdd(tile_counter, 1u);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= n_tiles) break;
+        unsigned long long ticket = 0ull;
+        if (lane == 0) ticket = atomicAdd(tile_counter, 1ull) - ticket_base;     // (every warp draws one ticket past the end)
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        if (ticket >= (unsigned long long)n_tiles) break;
+        const uint32_t tile = (uint32_t)ticket;
         const uint32_t ty = tile / tiles_x, tx = tile - ty * tiles_x;
         const uint32_t col = tx * kTile + px;
         const uint32_t colc = col < W ? col : W - 1u;     // clamp: out-of-frame lanes trace a duplicate ray
@@ -698,41 +697,30 @@ TracePlan plan_trace(uint32_t x, uint32_t rows, int n_slots, int n_ctas)
     return best;
 }
 
-cudaError_t launch_hoist(cudaStream_t st, const rtc_object* objs, const int32_t* sphere_obj, int n_spheres,
-                         int n_slots, const float cam[3], float* sph_fast, float4* sph_exact, float* grp_dmin,
-                         float4* grp_cone, float* grp_sin, unsigned int* counters, int n_counters, float4* obj_kd, int n_objs,
-                         const float* affine_m /* NULL, or the 12 floats of FrameParams::m: screen-affine layout */)
+// Tickets one launch draws from its counter: one per tile plus one per warp (the draw that tells a warp it is done).
+unsigned long long trace_tickets(uint32_t x, uint32_t rows, int n_ctas, int threads, int rays)
 {
-    HoistBasis hb;
-    hb.affine = affine_m != nullptr;
-    for (int i = 0; i < 3; ++i) {
-        hb.c0[i] = affine_m ? affine_m[4 * i + 0] : 0.0f;
-        hb.c1[i] = affine_m ? affine_m[4 * i + 1] : 0.0f;
-        hb.c2[i] = affine_m ? affine_m[4 * i + 2] : 0.0f;
-    }
-    int n = n_slots > n_counters ? n_slots : n_counters;
-    if (obj_kd != nullptr && n_objs > n) n = n_objs;
-    if (n <= 0) return cudaSuccess;
-    hoist_kernel<<<(n + 255) / 256, 256, 0, st>>>(objs, sphere_obj, n_spheres, n_slots, cam[0], cam[1], cam[2],
-                                                  sph_fast, sph_exact, grp_dmin, grp_cone, grp_sin, counters, n_counters,
-                                                  obj_kd, n_objs, hb);
-    return cudaGetLastError();
+    const unsigned long long W = x - 1u;
+    return ((W + kTile - 1) / kTile) * (((unsigned long long)rows + 2 * rays - 1) / (2 * rays)) + (unsigned long long)n_ctas * (threads / 32);
 }
 
-cudaError_t launch_trace(cudaStream_t st, int n_ctas, const FrameParams& fp, const float* g_fast, const float4* g_exact,
-                         const float* g_dmin, const float4* g_cone, const float* g_sin, const int32_t* sphere_obj, int n_spheres,
+cudaError_t launch_trace(cudaStream_t st, int n_ctas, const FrameParams& fp, const int32_t* sphere_obj, int n_spheres,
                          int n_slots, const rtc_object* objs, const int32_t* plane_obj, int n_planes, float* hit_t,
-                         int32_t* hit_idx, unsigned int* tile_counter, int carry_in, const float* light, uint8_t* shadow,
-                         int threads, bool cull, unsigned long long* groups_tested, const ShadeParams& sp, int shade_mode,
+                         int32_t* hit_idx, unsigned long long* tile_counter, unsigned long long ticket_base, int carry_in,
+                         const float* light, uint8_t* shadow, int threads, bool cull, unsigned long long* groups_tested,
+                         unsigned long long* stats_zero, const ShadeParams& sp, int shade_mode,
                          uint8_t* color, uint8_t* glyph, bool write_hits, const float4* obj_kd, bool affine, int rays)
 {
     const size_t smem = trace_smem_bytes(n_slots, threads, rays);
     const float l0 = light ? light[0] : 0.f, l1 = light ? light[1] : 0.f, l2 = light ? light[2] : 0.f;
+    HoistBasis hb;
+    hb.affine = affine ? 1 : 0;
+    for (int i = 0; i < 3; ++i) { hb.c0[i] = fp.m[4 * i + 0]; hb.c1[i] = fp.m[4 * i + 1]; hb.c2[i] = fp.m[4 * i + 2]; }
 #define RTC_TRACE_LAUNCH1(SH, T, C, A, R)                                                                                \
-    trace_kernel<SH, T, C, A, R><<<n_ctas, T, smem, st>>>(fp, g_fast, g_exact, g_dmin, g_cone, g_sin, sphere_obj, n_spheres, \
+    trace_kernel<SH, T, C, A, R><<<n_ctas, T, smem, st>>>(fp, hb, sphere_obj, n_spheres,                                 \
                                                           n_slots, objs, plane_obj, n_planes, hit_t, hit_idx, tile_counter, \
-                                                          carry_in, l0, l1, l2, shadow, groups_tested, sp, shade_mode, color, \
-                                                          glyph, write_hits ? 1 : 0, obj_kd)
+                                                          ticket_base, carry_in, l0, l1, l2, shadow, groups_tested, stats_zero, \
+                                                          sp, shade_mode, color, glyph, write_hits ? 1 : 0, obj_kd)
 #define RTC_TRACE_LAUNCH(SH, T, C, A)                                                                                    \
     do { if (rays == 8) RTC_TRACE_LAUNCH1(SH, T, C, A, 8); else RTC_TRACE_LAUNCH1(SH, T, C, A, 4); } while (0)
 #define RTC_TRACE_PICK(T)                                                                                                \
