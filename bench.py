@@ -5,7 +5,7 @@ Metric (BASELINE.json): Mrays/s (and frames/s) at 3840x2160, 1024 random spheres
 RGB_PIXEL mode, on 1/2/4/8 B200 with a row-band split gathered to GPU 0; ray-kernel fraction of
 the FP32 roofline; encoder fraction of HBM bandwidth.
 
-A "step" is one whole frame of the hot path: scene hoist -> ray kernel -> shade+quantise ->
+A "step" is one whole frame of the hot path: ray kernel (scene hoist, nearest hit, shade+quantise) ->
 (N>1: gather of the RGB8 bands to GPU 0) -> ANSI encode.  `value` is timed on the device with
 CUDA events (inputs resident in HBM); `e2e` is the same frame through the C-ABI with HOST
 buffers: scene + camera block uploaded, minimised stream copied back to pinned host memory.
@@ -581,8 +581,10 @@ def run_ours(args):
     else:
         line["per_device_ms"] = r["per_device_ms"]
         line["encode_ms_on_gpu0"] = r["encode_ms_on_gpu0"]
-        # hoist + trace(+shade epilogue) + count + emit per device (host gather) or hoist + trace per device and count + emit on GPU 0 (p2p)
-        line["gpu_launches"] = int((4 * N if args.gather == "host" else 2 * N + 2) * args.steps)
+        # per device: trace (scene hoist as its prologue, shade as its tile epilogue; with shadow rays: + shadow trace + shade), then
+        # count + emit per device (host gather) or once on GPU 0 (p2p)
+        tr = 3 if args.shadows else 1
+        line["gpu_launches"] = int(((tr + 2) * N if args.gather == "host" else tr * N + 2) * args.steps)
 
     if not args.headline_only:
         sub_steps = max(8, min(args.steps, 40))

@@ -137,7 +137,7 @@ typedef struct rtc_light {
 
 /* Per-stage device timings of the last rtc_render on this context (CUDA events). */
 typedef struct rtc_timings {
-    float prep_ms;    /* per-frame scene hoist (oc, c per sphere)          */
+    float prep_ms;    /* scene upload wait (the hoist runs inside kernel 1) */
     float trace_ms;   /* kernel 1: ray generation + nearest hit            */
     float shade_ms;   /* kernel 2: shade + quantise                        */
     float encode_ms;  /* kernel 3: ANSI encode (scan + scatter)            */
@@ -190,7 +190,7 @@ RTC_API int rtc_scene_count(rtc_ctx* ctx, uint32_t* n);
 RTC_API int rtc_update_objects(rtc_ctx* ctx, double dt, uint32_t flags);
 
 /* ---- frame: RayTracingManager::Update (RayTracingManager.cu:76-154) -------------------- */
-/* Asynchronous: enqueue hoist + trace + shade/quantise + ANSI encode for the whole frame
+/* Asynchronous: enqueue trace (+ shade/quantise) + ANSI encode (3 launches) for the whole frame
  * on the context's stream (replaces :83-127 and the host minimiser :146).                */
 RTC_API int rtc_render(rtc_ctx* ctx, const rtc_params* params, rtc_mode mode, uint32_t flags);
 /* Synchronise and return the minimised ANSI stream in a pinned host buffer owned by the

@@ -225,7 +225,7 @@ int do_encode(rtc_ctx* c, const uint8_t* d_color, const uint8_t* d_glyph, uint32
     return RTC_OK;
 }
 
-// hoist + trace + shade for rows [row0,row1) into colour/glyph planes (band-relative).
+// trace (scene hoist in its prologue, shade in its tile epilogue) for rows [row0,row1) into colour/glyph planes (band-relative).
 int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint32_t row0, uint32_t row1,
                 uint8_t* d_color, uint8_t* d_glyph, bool record_events)
 {

@@ -130,7 +130,7 @@ struct rtc_ctx {
 };
 
 namespace rtc {
-// hoist + trace (+ shade) for rows [row0,row1) into colour / glyph planes (band-relative), on c->stream.
+// trace (+ hoist, + shade) for rows [row0,row1) into colour / glyph planes (band-relative), on c->stream.
 int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint32_t row0, uint32_t row1,
                 uint8_t* d_color, uint8_t* d_glyph, bool record_events);
 // The ANSI encoder as one step (scratch, parity, the two launches), on c->stream.

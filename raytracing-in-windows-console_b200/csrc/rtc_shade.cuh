@@ -124,7 +124,7 @@ constexpr int kModeNormalsSaturate = 100 + RTC_RGB_NORMALS;   // `mode` of shade
 // One traced pixel -> colour key (RGB modes: R | G << 8 | B << 16; 8-bit modes: xterm-256 index) | glyph << 24.
 //   d: the ray direction (CalculateInitialDirection), t / idx: the accepted hit (idx < 0: none), shadowed: the shadow-ray
 //   extension found an occluder (ambient term only).  `objs` is the 64-byte object array, 16-byte aligned; obj_kd[i] is
-//   object i's colour / 255 (hoist kernel).
+//   object i's colour / 255 (computed by the host at scene upload, rtc_api.cu: upload_scene).
 //   (BIT8 / GLYPH follow from `mode`; they are separate arguments so that callers with compile-time modes fold them.)
 __device__ __forceinline__ uint32_t shade_pixel(const bool BIT8, const bool GLYPH, int mode, const ShadeParams& sp,
                                                 const rtc_object* __restrict__ objs, const float4* __restrict__ obj_kd, V3 cam,
