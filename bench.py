@@ -600,6 +600,22 @@ def run_ours(args):
                                         "output": "bit-identical to the brute-force frame (tests/test_gpu_parity.py::test_culling_is_invisible)"}
             except Exception as e:
                 line["with_culling"] = {"error": repr(e)}
+            # ---- and with the packet filter (RTC_FLAG_PACKET: the ray-sphere filter once per 8-ray packet), alone and on top
+            #      of the culling -- what the facade's RayTracingManager::Update runs by default; identical output ----------
+            for key, extra in (("with_packet_filter", rtc_b200.FLAG_PACKET), ("with_culling_and_packet_filter", rtc_b200.FLAG_PACKET | rtc_b200.FLAG_CULL)):
+                try:
+                    pf = rflags | extra
+                    rc = (measure_ctx(ctx, torch, stream, flush, objs, cams, mode, pf, sub_steps, 3) if N == 1 else
+                          measure_mgpu(m, objs, cams, mode, pf, sub_steps, 3))
+                    same = None
+                    if N == 1:
+                        same = parity_streams(ctx, objs, cams[:2], mode, pf) == parity_streams(ctx, objs, cams[:2], mode, rflags)
+                    line[key] = {"value": mr(rc["ms_per_step"]), "unit": "Mrays/s", "ms_per_step": rc["ms_per_step"],
+                                 "e2e": {"value": mr(rc["e2e_ms"]), "ms_per_step": rc["e2e_ms"]}, "stages_ms": rc.get("stages_ms"),
+                                 "stream_equals_per_ray_filter": same,
+                                 "output": "bit-identical to the per-ray filter (tests/test_gpu_parity.py::test_packet_filter_is_invisible)"}
+                except Exception as e:
+                    line[key] = {"error": repr(e)}
         # ---- N > 1: the other gather, and the N-GPU bytes against a single-GPU frame (outside every timed region) ----
         parity = {}
         if N > 1:

@@ -92,7 +92,14 @@ enum {
      * negative -> 0), its sources compiled for x86 wrap (cvttss2si, low byte).  The default follows the x86 build, the
      * one every parity fixture of this repository is pinned to; this flag selects the CUDA platform's conversion
      * (cross-checked against the reference's own kernels on a B200: tests/test_ref_cuda_crosscheck.py).           */
-    RTC_FLAG_NORMALS_SATURATE = 1u << 4
+    RTC_FLAG_NORMALS_SATURATE = 1u << 4,
+    /* Packet filter: the ray kernel's conservative ray-sphere filter runs once per PACKET -- the 8 (4) rays of one thread:
+     * one column, consecutive rows -- on the packet's first and last ray instead of on every ray; packets it flags go
+     * through the per-ray filter and the exact path as before.  Accepted hits, hence every output byte, are identical
+     * (tests/test_gpu_parity.py::test_packet_filter_is_invisible); 14 instead of 50 packed operations per 4 spheres x 8
+     * rays.  Like RTC_FLAG_CULL it changes what "a test" costs, so the brute-force roofline is quoted without it; the
+     * facade turns both on.  Primary rays under a camera matrix only (any other matrix: ignored).                  */
+    RTC_FLAG_PACKET = 1u << 5
 };
 
 /* == RayTracingCPUToGPUData (reference RayTracingManager.h:9-19) without the vptrs.

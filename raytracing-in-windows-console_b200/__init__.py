@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 from . import _types, scenes  # noqa: F401
-from ._types import (BIT_ASCII, BIT_PIXEL, FLAG_CULL, FLAG_KEEP_HITS, FLAG_NORMALS_SATURATE, FLAG_SHADOWS, FLAG_UPDATE_REF_LAUNCH_LIMIT, MODE_NAMES,  # noqa: F401
+from ._types import (BIT_ASCII, BIT_PIXEL, FLAG_CULL, FLAG_KEEP_HITS, FLAG_NORMALS_SATURATE, FLAG_PACKET, FLAG_SHADOWS, FLAG_UPDATE_REF_LAUNCH_LIMIT, MODE_NAMES,  # noqa: F401
                      OBJECT_DTYPE, RGB_ASCII, RGB_NORMALS, RGB_PIXEL, SDL, RtcParams, RtcTimings,
                      mode_bpp, mode_cell, mode_has_glyph, obj_ptr)
 

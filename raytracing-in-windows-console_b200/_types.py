@@ -65,6 +65,7 @@ FLAG_UPDATE_REF_LAUNCH_LIMIT = 2
 FLAG_CULL = 4
 FLAG_KEEP_HITS = 8
 FLAG_NORMALS_SATURATE = 16
+FLAG_PACKET = 32
 
 
 def mode_bpp(mode):

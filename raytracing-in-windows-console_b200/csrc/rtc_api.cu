@@ -258,6 +258,7 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
             const double dot = (double)fp0.m[a] * fp0.m[b] + (double)fp0.m[4 + a] * fp0.m[4 + b] + (double)fp0.m[8 + a] * fp0.m[8 + b];
             if (!(fabs(dot - (a == b ? 1.0 : 0.0)) < 1.0e-3)) affine = false;
         }
+    const bool packet = affine && (flags & RTC_FLAG_PACKET) != 0;   // (the packet filter is a form of the screen-affine one)
     const bool shadows = (flags & RTC_FLAG_SHADOWS) != 0 && mode != RTC_SDL && mode != RTC_RGB_NORMALS;
     // Without shadow rays the ray kernel shades + quantises in its tile epilogue (one launch, no hit-record round trip);
     // hit records are then written only on request.  With shadow rays the records feed the light-origin pass and the
@@ -269,7 +270,7 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
     c->hits_valid = false;
     if (n_px > 0) {
         const rtc::FrameParams fp = make_frame(p, row0, row1);
-        const rtc::TracePlan plan = rtc::plan_trace(p->x, row1 - row0, n_slots, c->sm_count);
+        const rtc::TracePlan plan = rtc::plan_trace(p->x, row1 - row0, n_slots, c->sm_count, packet);
         const int n_chunks = n_slots == 0 ? 1 : (n_slots + plan.max_slots - 1) / plan.max_slots;
         if (n_chunks > rtc::kMaxChunks) return fail(RTC_ERR_CAPACITY, "too many spheres (%d)", n_spheres);
         const unsigned long long tickets = rtc::trace_tickets(p->x, row1 - row0, c->sm_count, plan.threads, plan.rays);
@@ -286,7 +287,7 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
                                  sph, slots, c->d_objs.p, c->d_plane_obj.p, last ? n_planes : 0, c->d_hit_t.p,
                                  c->d_hit_idx.p, c->d_counters.p + ch, c->ticket_base[ch], ch > 0 ? 1 : 0, nullptr, nullptr, plan.threads,
                                  cull, stats, stats_zero, c->shade, fused && last ? shade_mode : -1, d_color, d_glyph,
-                                 !last || keep_hits, c->d_kd.p, affine, plan.rays));
+                                 !last || keep_hits, c->d_kd.p, affine, plan.rays, packet));
             c->ticket_base[ch] += tickets;
             c->last_launches++;
         }
@@ -302,7 +303,7 @@ int trace_shade(rtc_ctx* c, const rtc_params* p, int mode, uint32_t flags, uint3
                                      c->d_objs.p, c->d_plane_obj.p, last ? n_planes : 0,
                                      c->d_hit_t.p, c->d_hit_idx.p, c->d_counters.p + rtc::kMaxChunks + ch, c->ticket_base[rtc::kMaxChunks + ch],
                                      ch > 0 ? 1 : 0, c->shade.light, c->d_shadow.p, plan.threads, cull, stats + 1, stats_zero, c->shade, -1,
-                                     nullptr, nullptr, false, nullptr, false, plan.rays));
+                                     nullptr, nullptr, false, nullptr, false, plan.rays, false));
                 c->ticket_base[rtc::kMaxChunks + ch] += tickets;
                 c->last_launches++;
             }

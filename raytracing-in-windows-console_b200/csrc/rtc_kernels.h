@@ -12,7 +12,7 @@ struct ShadeParams;
 
 // The persistent ray-kernel CTA (one per SM) exists with 24 and with 28 warps; plan_trace picks per launch.
 struct TracePlan { int threads; int max_slots; int rays; };   // threads per CTA; sphere slots resident in shared memory per launch; rays per thread (8 or 4)
-TracePlan plan_trace(uint32_t x, uint32_t rows, int n_slots, int n_ctas);
+TracePlan plan_trace(uint32_t x, uint32_t rows, int n_slots, int n_ctas, bool packet);
 constexpr int kMaxChunks = 28;             // sphere-list chunks per pass (one ticket counter each): 69k spheres at 24 warps
 // Device counters of a context, all 64-bit, zeroed once at creation and never reset: [0 .. kMaxChunks) tile tickets of the
 // primary pass (one per sphere chunk), [kMaxChunks .. 2 kMaxChunks) of the shadow pass -- a launch draws its tickets above
@@ -32,7 +32,8 @@ cudaError_t launch_trace(cudaStream_t st, int n_ctas, const FrameParams& fp, con
                          unsigned long long* groups_tested, unsigned long long* stats_zero,
                          const ShadeParams& sp, int shade_mode /* >= 0: shade + quantise in the tile epilogue; -1: no */,
                          uint8_t* color, uint8_t* glyph, bool write_hits, const float4* obj_kd /* per object colour / 255 */,
-                         bool affine /* screen-affine packed filter (primary rays only) */, int rays /* per thread: 8 or 4 */);
+                         bool affine /* screen-affine packed filter (primary rays only) */, int rays /* per thread: 8 or 4 */,
+                         bool packet /* RTC_FLAG_PACKET: the filter on the end rays of every thread's packet (needs affine) */);
 
 // kernel 2 (rtc_shade.cu): stand-alone shade + quantise, used only after a shadow pass
 cudaError_t launch_shade(cudaStream_t st, const FrameParams& fp, const ShadeParams& sp, int mode,

@@ -47,12 +47,13 @@ namespace rtc {
 // Which packed filter the primary pass will run, and the columns of the inverse view matrix it needs.
 struct HoistBasis {
     int affine;          // 1: store (A, B, C) = g . (col0, col1, col2) per sphere; 0: store g itself
+    float eps;           // deflation of c: RTC_FILTER_EPS, or the packet filter's wider one (packet_eps)
     float c0[3], c1[3], c2[3];
 };
 
 // ---- kernel 1: trace --------------------------------------------------------------------
-// Rays per thread are a template parameter (kRays = 8 or 4): a thread owns one column and kRays rows (every other row) of
-// its warp's 16 x 2*kRays tile.  8 is the efficient shape (the per-column operand F of the screen-affine filter is
+// Rays per thread are a template parameter (kRays = 8 or 4): a thread owns one column and kRays consecutive rows (the
+// upper or the lower half) of its warp's 16 x 2*kRays tile.  8 is the efficient shape (the per-column operand F of the screen-affine filter is
 // amortised over 8 tests); 4 halves the work quantum for launches of only one or two tile waves (an 8-GPU band of a 4K
 // frame), where the phases of a warp's single tile -- ray set-up, sphere loop, shading epilogue -- would otherwise run in
 // lock step on all warps and not overlap (plan_trace).
@@ -150,7 +151,7 @@ __device__ __noinline__ void hoist_into_smem(const Smem sm, const rtc_object* __
         ocz = sub(camz, s.center[2]);
         const float oc2 = vdot(v3(ocx, ocy, ocz), v3(ocx, ocy, ocz));
         c = sub(oc2, mul(s.radius, s.radius));                          // Sphere.cu:37
-        const float cd = fmaf(-RTC_FILTER_EPS, oc2, c);                 // deflated c'
+        const float cd = fmaf(-hb.eps, oc2, c);                         // deflated c'
         const float inf = __int_as_float(0x7f800000);
         if (cd > 0.0f && cd < 3.0e38f) {
             if (hb.affine) {
@@ -280,6 +281,33 @@ __device__ __noinline__ uint32_t shade_call(const ShadeCtx* __restrict__ sc, flo
                        sc->sp, sc->objs, sc->kd, v3(sc->cam[0], sc->cam[1], sc->cam[2]), sc->far_dist, v3(dx, dy, dz), t, idx, false);
 }
 
+// The filter flagged something in group g: per-ray candidate mask from the non-finite u, group reject, exact path.
+template <int kThreads, int kRays>
+__device__ __forceinline__ void resolve_candidates(const Smem& s, const f32x2 (&u)[2][kRays], int g, const int32_t* __restrict__ sphere_obj,
+                                                   int n_slots, int tid)
+{
+    uint32_t mask = 0;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+#pragma unroll
+        for (int r = 0; r < kRays; ++r) {
+            float lo, hi;
+            unpack2(u[q][r], lo, hi);
+            mask |= not_finite(lo) ? (1u << (q * 16 + r * 2)) : 0u;
+            mask |= not_finite(hi) ? (1u << (q * 16 + r * 2 + 1)) : 0u;
+        }
+    }
+    if (mask) {
+        // Rays whose running best is already nearer than anything in this group of 4 spheres can offer
+        // drop out here (most candidates of a ray lie behind its nearest hit).
+        const float gd = s.gdmin[g];
+#pragma unroll
+        for (int r = 0; r < kRays; ++r)
+            if (gd > s.best_t[r * kThreads + tid]) mask &= ~(0x00030003u << (2 * r));
+        if (mask) exact_group<kThreads, kRays>(sphere_obj, n_slots, g, mask, tid);
+    }
+}
+
 // One group of 4 spheres (2 packed pairs) against the thread's 8 rays, operand-major, + 3 LDS.128 + one NaN check.
 //
 // AFFINE = false (shadow rays; primary rays under an ill-conditioned view matrix): u = 2^64 d . g, 3 packed ops per test
@@ -341,27 +369,89 @@ __device__ __forceinline__ void test_group(const Smem& s, uint32_t fa, int g, co
     }
     float alo, ahi;
     unpack2(add2(acc0, acc1), alo, ahi);
-    if (__any_sync(0xffffffffu, !(alo == ahi))) {                // NaN in either half (both are 0 otherwise)
-        uint32_t mask = 0;
+    if (__any_sync(0xffffffffu, !(alo == ahi)))                  // NaN in either half (both are 0 otherwise)
+        resolve_candidates<kThreads, kRays>(s, u, g, sphere_obj, n_slots, tid);
+}
+
+// ---- the PACKET form of the screen-affine filter (RTC_FLAG_PACKET) ------------------------------------------------------
+// A thread's kRays rays share their column and sit on consecutive rows, so along the packet only vy moves and
+//     h(vy) = d(vy) . oc / |oc|,   d = w / |w|,   w = (col2 + vx col0) + vy col1
+// is a smooth function of ONE variable with |h''| <= 5 |col1|^2 / |w|^2 <= 5.12 (3x3 orthonormal to 1e-3: |w| >= 0.999).
+// On an interval of length D a function stays within M D^2 / 8 of its chord, and a chord is largest at an end point:
+//     max_r |h(vy_r)|  <=  max(|h(vy_first)|, |h(vy_last)|) + 0.64 D^2 ,      D = |vy_first - vy_last|.
+// A reference hit on ray r needs |h(vy_r)| >= sqrt(kappa - eps0), kappa = c / |oc|^2, eps0 = 44.6 u (DESIGN.md "filter
+// bound"); sqrt(kappa - eps0) - sqrt(kappa - E) >= (E - eps0) / 2 for kappa <= 1, so with the spheres hoisted under the
+// deflation E = 1e-5 + 1.5 D^2 (packet_eps; >= eps0 + 2 * 0.64 D^2 with the per-ray filter's own head-room kept) the
+// per-ray filter evaluated on the FIRST and the LAST ray of the packet alone overflows whenever any ray of the packet
+// can hit: 7 packed ops per sphere pair and 8 rays (F; t and u at both ends; two sticky accumulates) instead of 25.
+// Flagged groups (about one warp iteration in a hundred) run the per-ray filter of test_group out of line, on the same
+// operands, and go on to the exact path as before: the accepted hits are the reference's, bit for bit.
+// (vy_r is monotone in r -- the roundings of cy and vy are monotone, clamped rows repeat the last row -- so every ray of
+// the packet lies between its ends.)
+template <int kRays>
+struct RayOps {
+    float vx;
+    float vy[kRays];
+    float sc[kRays];       // 2^64 / |w_r|
+};
+
+template <int kThreads, int kRays>
+__device__ __noinline__ void packet_slow_group(uint32_t fa, int g, const RayOps<kRays> ro, const int32_t* __restrict__ sphere_obj, int n_slots, int tid)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Smem s = carve(smem_raw, n_slots, kThreads, kRays);
+    const float4 FX = lds128(fa), FY = lds128(fa + 16u), FZ = lds128(fa + 32u);
+    f32x2 u[2][kRays];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < 2; ++q) {
+        const f32x2 A = q ? pack2(FX.z, FX.w) : pack2(FX.x, FX.y);
+        const f32x2 B = q ? pack2(FY.z, FY.w) : pack2(FY.x, FY.y);
+        const f32x2 C = q ? pack2(FZ.z, FZ.w) : pack2(FZ.x, FZ.y);
+        const f32x2 F = fma2(pack2(ro.vx, ro.vx), A, C);
 #pragma unroll
-            for (int r = 0; r < kRays; ++r) {
-                float lo, hi;
-                unpack2(u[q][r], lo, hi);
-                mask |= not_finite(lo) ? (1u << (q * 16 + r * 2)) : 0u;
-                mask |= not_finite(hi) ? (1u << (q * 16 + r * 2 + 1)) : 0u;
-            }
-        }
-        if (mask) {
-            // Rays whose running best is already nearer than anything in this group of 4 spheres can offer
-            // drop out here (most candidates of a ray lie behind its nearest hit).
-            const float gd = s.gdmin[g];
+        for (int r = 0; r < kRays; ++r) u[q][r] = mul2(fma2(pack2(ro.vy[r], ro.vy[r]), B, F), pack2(ro.sc[r], ro.sc[r]));
+    }
+    resolve_candidates<kThreads, kRays>(s, u, g, sphere_obj, n_slots, tid);
+}
+
+// NaN-sticky flag of one group of 4 spheres against the two end rays of the thread's packet: 14 packed ops + 3 LDS.128.
+struct PacketEnds { f32x2 vx, vy0, vy1, s0, s1; };
+__device__ __forceinline__ f32x2 packet_flag(uint32_t fa, const PacketEnds& e)
+{
+    const f32x2 ZERO2 = pack2(0.0f, 0.0f);
+    const float4 FX = lds128(fa), FY = lds128(fa + 16u), FZ = lds128(fa + 32u);   // warp-broadcast
+    f32x2 acc0 = ZERO2, acc1 = ZERO2;
 #pragma unroll
-            for (int r = 0; r < kRays; ++r)
-                if (gd > s.best_t[r * kThreads + tid]) mask &= ~(0x00030003u << (2 * r));
-            if (mask) exact_group<kThreads, kRays>(sphere_obj, n_slots, g, mask, tid);
-        }
+    for (int q = 0; q < 2; ++q) {
+        const f32x2 A = q ? pack2(FX.z, FX.w) : pack2(FX.x, FX.y);
+        const f32x2 B = q ? pack2(FY.z, FY.w) : pack2(FY.x, FY.y);
+        const f32x2 C = q ? pack2(FZ.z, FZ.w) : pack2(FZ.x, FZ.y);
+        const f32x2 F = fma2(e.vx, A, C);
+        const f32x2 u0 = mul2(fma2(e.vy0, B, F), e.s0);
+        const f32x2 u1 = mul2(fma2(e.vy1, B, F), e.s1);
+        acc0 = fma2(u0, ZERO2, acc0);                          // inf * 0 -> NaN, sticky
+        acc1 = fma2(u1, ZERO2, acc1);
+    }
+    return add2(acc0, acc1);
+}
+
+// Two groups per NaN check (g1 < 0: one group).
+template <int kThreads, int kRays>
+__device__ __forceinline__ void test_packet_groups(uint32_t fast_base, int g0, int g1, const PacketEnds& e, const RayOps<kRays>& ro,
+                                                   const int32_t* __restrict__ sphere_obj, int n_slots, int tid)
+{
+    const uint32_t fa0 = fast_base + 48u * (uint32_t)g0;
+    const f32x2 f0 = packet_flag(fa0, e);
+    f32x2 f1 = pack2(0.0f, 0.0f);
+    const uint32_t fa1 = fast_base + 48u * (uint32_t)(g1 < 0 ? g0 : g1);
+    if (g1 >= 0) f1 = packet_flag(fa1, e);
+    float alo, ahi;
+    unpack2(add2(f0, f1), alo, ahi);
+    if (__any_sync(0xffffffffu, !(alo == ahi))) {                // NaN somewhere (both halves are 0 otherwise)
+        unpack2(f0, alo, ahi);
+        if (__any_sync(0xffffffffu, !(alo == ahi))) packet_slow_group<kThreads, kRays>(fa0, g0, ro, sphere_obj, n_slots, tid);
+        unpack2(f1, alo, ahi);
+        if (g1 >= 0 && __any_sync(0xffffffffu, !(alo == ahi))) packet_slow_group<kThreads, kRays>(fa1, g1, ro, sphere_obj, n_slots, tid);
     }
 }
 
@@ -375,7 +465,8 @@ __device__ __forceinline__ void test_group(const Smem& s, uint32_t fa, int g, co
 // CULL = true (RTC_FLAG_CULL): per warp tile, the groups of 4 spheres whose bounding cone (hoisted) misses the tile's
 //   ray cone are skipped -- results are identical, far fewer tests are executed (the count is reported).
 // AFFINE = true: the screen-affine packed filter (see test_group); primary rays only.
-template <bool SHADOW, int kThreads, bool CULL, bool AFFINE, int kRays>
+// PACKET = true (RTC_FLAG_PACKET; needs AFFINE): the filter runs on the two end rays of every thread's packet (test_packet_groups).
+template <bool SHADOW, int kThreads, bool CULL, bool AFFINE, int kRays, bool PACKET>
 __global__ void __launch_bounds__(kThreads, 1)
 trace_kernel(const FrameParams fp, const HoistBasis hb,
              const int32_t* __restrict__ sphere_obj, int n_spheres, int n_slots,
@@ -429,7 +520,7 @@ trace_kernel(const FrameParams fp, const HoistBasis hb,
         float ex[kRays], ey[kRays], ez[kRays];            // ray direction scaled by 2^64 (exact)
 #pragma unroll
         for (int r = 0; r < kRays; ++r) {
-            uint32_t row = fp.row0 + ty * kTileH + py + 2u * r;
+            uint32_t row = fp.row0 + ty * kTileH + py * kRays + r;
             if (row >= fp.row1) row = fp.row1 - 1u;
             float vx, vy, inv;
             V3 d = initial_direction_ex(fp, row, colc, vx, vy, inv);
@@ -475,7 +566,7 @@ trace_kernel(const FrameParams fp, const HoistBasis hb,
             if (!__any_sync(0xffffffffu, any)) {
 #pragma unroll
                 for (int r = 0; r < kRays; ++r) {
-                    const uint32_t row = fp.row0 + ty * kTileH + py + 2u * r;
+                    const uint32_t row = fp.row0 + ty * kTileH + py * kRays + r;
                     if (row < fp.row1 && col < W && !carry_in) shadow[(size_t)(row - fp.row0) * W + col] = 0;
                 }
                 continue;
@@ -483,10 +574,26 @@ trace_kernel(const FrameParams fp, const HoistBasis hb,
         }
 
         // ---- hot loop over groups of 4 spheres ---------------------------------------------------------
+        PacketEnds pe;
+        RayOps<kRays> ro;
+        if (PACKET) {
+            pe.vx = pack2(ex[0], ex[0]);
+            pe.vy0 = pack2(ey[0], ey[0]); pe.vy1 = pack2(ey[kRays - 1], ey[kRays - 1]);
+            pe.s0 = pack2(ez[0], ez[0]);  pe.s1 = pack2(ez[kRays - 1], ez[kRays - 1]);
+            ro.vx = ex[0];
+#pragma unroll
+            for (int r = 0; r < kRays; ++r) { ro.vy[r] = ey[r]; ro.sc[r] = ez[r]; }
+        }
         if (!CULL) {
-            uint32_t fa = fast_base;
+            if (PACKET) {
+#pragma unroll 1
+                for (int g = 0; g < n_groups; g += 2)
+                    test_packet_groups<kThreads, kRays>(fast_base, g, g + 1 < n_groups ? g + 1 : -1, pe, ro, sphere_obj, n_slots, tid);
+            } else {
+                uint32_t fa = fast_base;
 #pragma unroll 2
-            for (int g = 0; g < n_groups; ++g, fa += 48u) test_group<kThreads, AFFINE, kRays>(s, fa, g, ex, ey, ez, sphere_obj, n_slots, tid);
+                for (int g = 0; g < n_groups; ++g, fa += 48u) test_group<kThreads, AFFINE, kRays>(s, fa, g, ex, ey, ez, sphere_obj, n_slots, tid);
+            }
             my_groups += (unsigned int)n_groups;
         } else {
             // Bounding cone of this warp's (active) rays: axis = normalised sum of the directions, cos(theta) = the
@@ -535,6 +642,12 @@ trace_kernel(const FrameParams fp, const HoistBasis hb,
                 while (m) {
                     const int g0 = gb + __ffs(m) - 1;
                     m &= m - 1;
+                    if (PACKET) {
+                        int g1 = -1;
+                        if (m) { g1 = gb + __ffs(m) - 1; m &= m - 1; }
+                        test_packet_groups<kThreads, kRays>(fast_base, g0, g1, pe, ro, sphere_obj, n_slots, tid);
+                        continue;
+                    }
                     test_group<kThreads, AFFINE, kRays>(s, fast_base + 48u * (uint32_t)g0, g0, ex, ey, ez, sphere_obj, n_slots, tid);
                     if (m) {                                     // a second group back to back: the unroll-by-2 of the brute-force loop
                         const int g1 = gb + __ffs(m) - 1;
@@ -567,7 +680,7 @@ trace_kernel(const FrameParams fp, const HoistBasis hb,
         if (SHADOW || write_hits) {
 #pragma unroll
             for (int r = 0; r < kRays; ++r) {
-                const uint32_t row = fp.row0 + ty * kTileH + py + 2u * r;
+                const uint32_t row = fp.row0 + ty * kTileH + py * kRays + r;
                 if (row < fp.row1 && col < W) {
                     const size_t pix = (size_t)(row - fp.row0) * W + col;
                     const int slot = r * kThreads + tid;
@@ -589,7 +702,7 @@ trace_kernel(const FrameParams fp, const HoistBasis hb,
             const bool has_gl = shade_mode == RTC_BIT_ASCII || shade_mode == RTC_RGB_ASCII;
             const uint32_t bpp = bit8 ? 1u : 3u;
             // The tile's planes are staged in the warp's own div2A runs (dead after the sphere loop; one 128-byte run per
-            // r holds tile rows 2r and 2r+1: colour at py * 16 * bpp, glyphs at 96 + py * 16) and leave as 16-byte
+            // r holds tile rows r and kRays + r: colour at py * 16 * bpp, glyphs at 96 + py * 16) and leave as 16-byte
             // stores -- which is what a peer GPU's memory wants when the band is written over NVLink.
             const bool fast = (W & 15u) == 0u && ((reinterpret_cast<uintptr_t>(color) | reinterpret_cast<uintptr_t>(glyph)) & 15u) == 0u;
             __syncwarp();
@@ -600,7 +713,7 @@ trace_kernel(const FrameParams fp, const HoistBasis hb,
                 const int idx = s.best_idx[slot];
                 uint32_t v = (bit8 ? 16u : 0u) | ((uint32_t)' ' << 24);
                 if (t <= fp.far_dist) v = shade_call(s.shade, s.dirx[slot], s.diry[slot], s.dirz[slot], t, idx);
-                const uint32_t row = fp.row0 + ty * kTileH + py + 2u * r;
+                const uint32_t row = fp.row0 + ty * kTileH + py * kRays + r;
                 if (fast) {
                     unsigned char* run = reinterpret_cast<unsigned char*>(s.div2A + r * kThreads + (tid & ~31));
                     unsigned char* pc = run + (py * 16u + px) * bpp;
@@ -622,16 +735,18 @@ trace_kernel(const FrameParams fp, const HoistBasis hb,
                     const uint32_t rho = i / parts, part = i - rho * parts;      // tile row, piece
                     const uint32_t row = row_t + rho;
                     if (row < fp.row1) {
-                        const unsigned char* run = reinterpret_cast<const unsigned char*>(s.div2A + (rho >> 1) * kThreads + (tid & ~31));
-                        const uint4 q = *reinterpret_cast<const uint4*>(run + (rho & 1u) * 16u * bpp + part * 16u);
+                        const uint32_t hy = rho / (uint32_t)kRays, hr = rho - hy * (uint32_t)kRays;   // half of the tile, ray index
+                        const unsigned char* run = reinterpret_cast<const unsigned char*>(s.div2A + hr * kThreads + (tid & ~31));
+                        const uint4 q = *reinterpret_cast<const uint4*>(run + hy * 16u * bpp + part * 16u);
                         *reinterpret_cast<uint4*>(color + ((size_t)(row - fp.row0) * W + tx * kTile) * bpp + part * 16u) = q;
                     }
                 }
                 if (has_gl && lane < (int)kTileH) {
                     const uint32_t row = row_t + (uint32_t)lane;
                     if (row < fp.row1) {
-                        const unsigned char* run = reinterpret_cast<const unsigned char*>(s.div2A + (lane >> 1) * kThreads + (tid & ~31));
-                        const uint4 q = *reinterpret_cast<const uint4*>(run + 96u + (lane & 1) * 16u);
+                        const uint32_t hy = (uint32_t)lane / (uint32_t)kRays, hr = (uint32_t)lane - hy * (uint32_t)kRays;
+                        const unsigned char* run = reinterpret_cast<const unsigned char*>(s.div2A + hr * kThreads + (tid & ~31));
+                        const uint4 q = *reinterpret_cast<const uint4*>(run + 96u + hy * 16u);
                         *reinterpret_cast<uint4*>(glyph + (size_t)(row - fp.row0) * W + tx * kTile) = q;
                     }
                 }
@@ -645,12 +760,13 @@ trace_kernel(const FrameParams fp, const HoistBasis hb,
 cudaError_t configure_trace()   // per device, once per context
 {
     cudaError_t e;
-#define RTC_TRACE_ATTR1(SH, T, C, A, R)                                                                                      \
-    if ((e = cudaFuncSetAttribute(trace_kernel<SH, T, C, A, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e
-#define RTC_TRACE_ATTR(SH, T, C, A) RTC_TRACE_ATTR1(SH, T, C, A, 8); RTC_TRACE_ATTR1(SH, T, C, A, 4)
-    RTC_TRACE_ATTR(false, 768, false, false); RTC_TRACE_ATTR(true, 768, false, false); RTC_TRACE_ATTR(false, 896, false, false); RTC_TRACE_ATTR(true, 896, false, false);
-    RTC_TRACE_ATTR(false, 768, true, false);  RTC_TRACE_ATTR(true, 768, true, false);  RTC_TRACE_ATTR(false, 896, true, false);  RTC_TRACE_ATTR(true, 896, true, false);
-    RTC_TRACE_ATTR(false, 768, false, true);  RTC_TRACE_ATTR(false, 896, false, true); RTC_TRACE_ATTR(false, 768, true, true);   RTC_TRACE_ATTR(false, 896, true, true);
+#define RTC_TRACE_ATTR1(SH, T, C, A, R, P)                                                                                   \
+    if ((e = cudaFuncSetAttribute(trace_kernel<SH, T, C, A, R, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e
+#define RTC_TRACE_ATTR(SH, T, C, A, P) RTC_TRACE_ATTR1(SH, T, C, A, 8, P); RTC_TRACE_ATTR1(SH, T, C, A, 4, P)
+    RTC_TRACE_ATTR(false, 768, false, false, false); RTC_TRACE_ATTR(true, 768, false, false, false); RTC_TRACE_ATTR(false, 896, false, false, false); RTC_TRACE_ATTR(true, 896, false, false, false);
+    RTC_TRACE_ATTR(false, 768, true, false, false);  RTC_TRACE_ATTR(true, 768, true, false, false);  RTC_TRACE_ATTR(false, 896, true, false, false);  RTC_TRACE_ATTR(true, 896, true, false, false);
+    RTC_TRACE_ATTR(false, 768, false, true, false);  RTC_TRACE_ATTR(false, 896, false, true, false); RTC_TRACE_ATTR(false, 768, true, true, false);   RTC_TRACE_ATTR(false, 896, true, true, false);
+    RTC_TRACE_ATTR(false, 768, false, true, true);   RTC_TRACE_ATTR(false, 896, false, true, true);  RTC_TRACE_ATTR(false, 768, true, true, true);    RTC_TRACE_ATTR(false, 896, true, true, true);
 #undef RTC_TRACE_ATTR
 #undef RTC_TRACE_ATTR1
     return cudaSuccess;
@@ -670,7 +786,7 @@ size_t trace_smem_bytes(int n_slots, int threads, int rays)
 // 271 rows of a 4K frame 0.151 ms with 8 rays, 0.168 with 4; 136 rows 0.133 against 0.095), so they only pay when the
 // launch is less than about half a wave of 16 x 16 tiles -- console-sized frames, the reference's own use case.  More warps
 // or rays leave less shared memory for spheres, i.e. more launches over a long sphere list -- priced in per chunk.
-TracePlan plan_trace(uint32_t x, uint32_t rows, int n_slots, int n_ctas)
+TracePlan plan_trace(uint32_t x, uint32_t rows, int n_slots, int n_ctas, bool packet)
 {
     static const char* force = getenv("RTC_TRACE_THREADS_FORCE");      // experiments only
     static const char* force_rays = getenv("RTC_TRACE_RAYS_FORCE");
@@ -688,7 +804,9 @@ TracePlan plan_trace(uint32_t x, uint32_t rows, int n_slots, int n_ctas)
             const long long per_wave = (long long)n_ctas * w;
             const double waves = (double)((tiles + per_wave - 1) / per_wave);
             // per chunk: the sphere loop over its share of the list + a fixed ray set-up / write-back worth ~40 sphere tests
-            const double tile_time = w * rays * ((double)(n_slots > 0 ? n_slots : 1) * (rays == 4 ? 1.14 : 1.0) + 40.0 * chunks);
+            // (packet filter: 14 packed ops per group and packet whatever its length, against 50 per 8 rays)
+            const double per_test = packet ? (rays == 4 ? 0.62 : 0.30) : (rays == 4 ? 1.14 : 1.0);
+            const double tile_time = w * rays * ((double)(n_slots > 0 ? n_slots : 1) * per_test + 40.0 * chunks);
             const double cost = waves * tile_time;
             if (best_cost < 0.0 || cost < best_cost * 0.999) { best_cost = cost; best.threads = w * 32; best.max_slots = max_slots; best.rays = rays; }
         }
@@ -704,33 +822,46 @@ unsigned long long trace_tickets(uint32_t x, uint32_t rows, int n_ctas, int thre
     return ((W + kTile - 1) / kTile) * (((unsigned long long)rows + 2 * rays - 1) / (2 * rays)) + (unsigned long long)n_ctas * (threads / 32);
 }
 
+// Deflation of c for the packet filter (see test_packet_groups): E = 1e-5 + 1.5 D^2, D = the vy span of one packet.
+// vy = cy e2, cy = (y - 2 row) / y (RayTracing.cu:16,20): consecutive rows are 2 |e2| / y apart (+ the rounding of cy and vy).
+static float packet_eps(const FrameParams& fp, int rays)
+{
+    const double e2 = fabs((double)fp.e2);
+    const double D = (double)(rays - 1) * (2.0 * e2 / (double)fp.fy) * 1.0001 + 1.0e-6 * (1.0 + e2);
+    const double E = 1.0e-5 + 1.5 * D * D;
+    return (float)(E < 4.0 ? E : 4.0);                           // (E >= kappa: the sphere is an unconditional candidate)
+}
+
 cudaError_t launch_trace(cudaStream_t st, int n_ctas, const FrameParams& fp, const int32_t* sphere_obj, int n_spheres,
                          int n_slots, const rtc_object* objs, const int32_t* plane_obj, int n_planes, float* hit_t,
                          int32_t* hit_idx, unsigned long long* tile_counter, unsigned long long ticket_base, int carry_in,
                          const float* light, uint8_t* shadow, int threads, bool cull, unsigned long long* groups_tested,
                          unsigned long long* stats_zero, const ShadeParams& sp, int shade_mode,
-                         uint8_t* color, uint8_t* glyph, bool write_hits, const float4* obj_kd, bool affine, int rays)
+                         uint8_t* color, uint8_t* glyph, bool write_hits, const float4* obj_kd, bool affine, int rays, bool packet)
 {
     const size_t smem = trace_smem_bytes(n_slots, threads, rays);
     const float l0 = light ? light[0] : 0.f, l1 = light ? light[1] : 0.f, l2 = light ? light[2] : 0.f;
+    if (light && affine) return cudaErrorInvalidValue;           // shadow rays do not come from a pixel grid
+    if (packet && !affine) return cudaErrorInvalidValue;         // the packet filter is a form of the screen-affine one
+    if (rays != 8 && rays != 4) return cudaErrorInvalidValue;
     HoistBasis hb;
     hb.affine = affine ? 1 : 0;
+    hb.eps = packet ? packet_eps(fp, rays) : RTC_FILTER_EPS;
     for (int i = 0; i < 3; ++i) { hb.c0[i] = fp.m[4 * i + 0]; hb.c1[i] = fp.m[4 * i + 1]; hb.c2[i] = fp.m[4 * i + 2]; }
-#define RTC_TRACE_LAUNCH1(SH, T, C, A, R)                                                                                \
-    trace_kernel<SH, T, C, A, R><<<n_ctas, T, smem, st>>>(fp, hb, sphere_obj, n_spheres,                                 \
-                                                          n_slots, objs, plane_obj, n_planes, hit_t, hit_idx, tile_counter, \
-                                                          ticket_base, carry_in, l0, l1, l2, shadow, groups_tested, stats_zero, \
-                                                          sp, shade_mode, color, glyph, write_hits ? 1 : 0, obj_kd)
-#define RTC_TRACE_LAUNCH(SH, T, C, A)                                                                                    \
-    do { if (rays == 8) RTC_TRACE_LAUNCH1(SH, T, C, A, 8); else RTC_TRACE_LAUNCH1(SH, T, C, A, 4); } while (0)
+#define RTC_TRACE_LAUNCH1(SH, T, C, A, R, P)                                                                             \
+    trace_kernel<SH, T, C, A, R, P><<<n_ctas, T, smem, st>>>(fp, hb, sphere_obj, n_spheres,                              \
+                                                             n_slots, objs, plane_obj, n_planes, hit_t, hit_idx, tile_counter, \
+                                                             ticket_base, carry_in, l0, l1, l2, shadow, groups_tested, stats_zero, \
+                                                             sp, shade_mode, color, glyph, write_hits ? 1 : 0, obj_kd)
+#define RTC_TRACE_LAUNCH(SH, T, C, A, P)                                                                                 \
+    do { if (rays == 8) RTC_TRACE_LAUNCH1(SH, T, C, A, 8, P); else RTC_TRACE_LAUNCH1(SH, T, C, A, 4, P); } while (0)
 #define RTC_TRACE_PICK(T)                                                                                                \
     do {                                                                                                                 \
-        if (light) { if (cull) RTC_TRACE_LAUNCH(true, T, true, false); else RTC_TRACE_LAUNCH(true, T, false, false); }   \
-        else if (affine) { if (cull) RTC_TRACE_LAUNCH(false, T, true, true); else RTC_TRACE_LAUNCH(false, T, false, true); } \
-        else       { if (cull) RTC_TRACE_LAUNCH(false, T, true, false); else RTC_TRACE_LAUNCH(false, T, false, false); } \
+        if (light) { if (cull) RTC_TRACE_LAUNCH(true, T, true, false, false); else RTC_TRACE_LAUNCH(true, T, false, false, false); } \
+        else if (packet) { if (cull) RTC_TRACE_LAUNCH(false, T, true, true, true); else RTC_TRACE_LAUNCH(false, T, false, true, true); } \
+        else if (affine) { if (cull) RTC_TRACE_LAUNCH(false, T, true, true, false); else RTC_TRACE_LAUNCH(false, T, false, true, false); } \
+        else       { if (cull) RTC_TRACE_LAUNCH(false, T, true, false, false); else RTC_TRACE_LAUNCH(false, T, false, false, false); } \
     } while (0)
-    if (light && affine) return cudaErrorInvalidValue;           // shadow rays do not come from a pixel grid
-    if (rays != 8 && rays != 4) return cudaErrorInvalidValue;
     if (threads == 896) RTC_TRACE_PICK(896);
     else if (threads == 768) RTC_TRACE_PICK(768);
     else return cudaErrorInvalidValue;

@@ -35,7 +35,7 @@ void RayTracing::RayTrace(const dim3&, const dim3&, Object3D* DEVICE_MEMORY_PTR 
     p.cam_pos[0] = params->camPos.x; p.cam_pos[1] = params->camPos.y; p.cam_pos[2] = params->camPos.z;
     p.x = (uint32_t)params->x; p.y = (uint32_t)params->y;
     p.element1 = params->element1; p.element2 = params->element2; p.cam_far = params->camFarDist;
-    gpuErrchk(rtc_trace_raw(be->ctx, &p, (rtc_mode)mode, RTC_FLAG_CULL, resultArray));
+    gpuErrchk(rtc_trace_raw(be->ctx, &p, (rtc_mode)mode, RTC_FLAG_CULL | RTC_FLAG_PACKET, resultArray));
 }
 
 void RayTracing::Synchronize(Object3D* DEVICE_MEMORY_PTR const objects)

@@ -28,6 +28,7 @@ RayTracingManager::RayTracingManager()
     if (b->ctx) gpuErrchk(rtc_resize(b->ctx, (uint32_t)PrintMachine::GetWidth(), (uint32_t)PrintMachine::GetHeight()));
     if (getenv("RTC_FACADE_SYNC")) m_pipelined = false;
     if (getenv("RTC_FACADE_NO_CULL")) m_culling = false;
+    if (getenv("RTC_FACADE_NO_PACKET")) m_packets = false;
 }
 
 RayTracingManager::~RayTracingManager() {}   // (a frame still in flight is dropped with the context)
@@ -47,7 +48,7 @@ void RayTracingManager::Update(const RayTracingCPUToGPUData& params, const Devic
     p.cam_pos[0] = params.camPos.x; p.cam_pos[1] = params.camPos.y; p.cam_pos[2] = params.camPos.z;
     p.x = (uint32_t)params.x; p.y = (uint32_t)params.y;
     p.element1 = params.element1; p.element2 = params.element2; p.cam_far = params.camFarDist;
-    uint32_t flags = (m_shadows ? RTC_FLAG_SHADOWS : 0u) | (m_culling ? RTC_FLAG_CULL : 0u) |
+    uint32_t flags = (m_shadows ? RTC_FLAG_SHADOWS : 0u) | (m_culling ? RTC_FLAG_CULL : 0u) | (m_packets ? RTC_FLAG_PACKET : 0u) |
                      (m_fixLaunchLimit ? 0u : RTC_FLAG_UPDATE_REF_LAUNCH_LIMIT);
     const char* stream = nullptr;
     size_t size = 0;

@@ -35,6 +35,9 @@ public:
     // Per-tile sphere culling (RTC_FLAG_CULL): identical frames, far fewer ray-sphere tests.  ON by default -- it is
     // bit-identical by test (tests/test_gpu_parity.py::test_culling_is_invisible).
     void SetCulling(bool on) { m_culling = on; }
+    // Packet filter (RTC_FLAG_PACKET): the ray-sphere filter once per 8-ray packet instead of once per ray; identical
+    // frames (tests/test_gpu_parity.py::test_packet_filter_is_invisible).  ON by default (RTC_FACADE_NO_PACKET=1: off).
+    void SetPacketFilter(bool on) { m_packets = on; }
     // Pipelined sink (rtc_submit / rtc_collect, rtc_mgpu_submit / rtc_mgpu_collect): Update(k) enqueues frame k and hands
     // frame k-1 to PrintMachine, so the copy of k-1 to the host runs under the kernels of k -- one frame of latency, like
     // the reference's own print thread behind SetDataInBackBuffer.  ON by default (RTC_FACADE_SYNC=1 or
@@ -47,6 +50,7 @@ private:
     RenderingMode currentRenderingMode = BIT_ASCII;    // reference RayTracingManager.h:53
     bool m_shadows = false;
     bool m_culling = true;
+    bool m_packets = true;
     bool m_pipelined = true;
     bool m_inFlight = false;
     void* m_backend = nullptr;

@@ -425,6 +425,63 @@ def test_culling_is_invisible(ctx, oracle, rtc):
     assert brute >= n_px * 1024 and culled < brute // 4, (brute, culled)
 
 
+def test_packet_filter_is_invisible(ctx, oracle, rtc):
+    """RTC_FLAG_PACKET (the ray-sphere filter on the first and last ray of every thread's 8-ray packet instead of on every
+    ray) must not change a hit record, colour or stream byte: whole frames against the oracle, alone and with culling /
+    shadow rays, 8-ray and 4-ray packets (console-sized frames), chunked sphere lists, camera inside the cloud, and --
+    the case the chord bound exists for -- spheres much smaller than a packet, sitting between its end rays."""
+    from rtc_b200._types import FLAG_PACKET
+    objs = scenes.config_scene("config2_1080p_64")
+    p = scenes.config_camera("config2_1080p_64")
+    check_frame(ctx, oracle, objs, p, RGB_PIXEL, flags=FLAG_PACKET)
+    check_frame(ctx, oracle, objs, p, RGB_ASCII, flags=FLAG_PACKET | FLAG_CULL | FLAG_SHADOWS)
+    check_frame(ctx, oracle, objs, p, BIT_PIXEL, flags=FLAG_PACKET | FLAG_CULL)
+    small = rtc.camera_params(64, 20, (0, 0, 0), (0, PI32, 0))
+    for mode in (RGB_PIXEL, BIT_ASCII):
+        check_frame(ctx, oracle, scenes.default_scene(), small, mode, flags=FLAG_PACKET)
+        check_frame(ctx, oracle, scenes.default_scene(), small, mode, flags=FLAG_PACKET | FLAG_CULL)
+    check_frame(ctx, oracle, scenes.default_scene(), rtc.camera_params(400, 150, (0, 0, 0), (0, PI32, 0)), RGB_ASCII, flags=FLAG_PACKET)
+    many = scenes.random_spheres(9001, 33)
+    q = rtc.camera_params(241, 120, (0, 0, -120), (0, PI32, 0), 1.0 / 240)
+    check_frame(ctx, oracle, many, q, RGB_PIXEL, flags=FLAG_PACKET)
+    check_frame(ctx, oracle, many, q, RGB_PIXEL, flags=FLAG_PACKET | FLAG_CULL)
+    inside = rtc.camera_params(161, 90, (3, -2, 5), (0.3, 1.0, 0), 1.0 / 160)
+    check_frame(ctx, oracle, scenes.random_spheres(700, 34), inside, RGB_PIXEL, flags=FLAG_PACKET)
+    check_frame(ctx, oracle, scenes.random_spheres(700, 34), inside, RGB_PIXEL, flags=FLAG_PACKET | FLAG_CULL | FLAG_SHADOWS)
+    # sub-pixel to few-pixel spheres all over a tall frame (a pixel is 1.07e-3 rad high; radii 2e-4 .. 4e-3 rad), rolled and
+    # pitched camera, ragged width: many of them lie strictly between the end rays of a packet
+    rng = np.random.default_rng(11)
+    n_s = 600
+    u = rng.normal(size=(n_s, 3)); u[:, 2] = np.abs(u[:, 2]) + 0.6
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    dist = rng.uniform(30.0, 200.0, n_s)
+    rad = dist * rng.choice([2e-4, 5e-4, 1e-3, 2e-3, 4e-3], n_s)
+    tiny = np.array([scenes.make_sphere(tuple(float(v) for v in (u[i] * dist[i])), float(rad[i]),
+                                        (int(rng.integers(0, 255)), int(rng.integers(0, 255)), int(rng.integers(0, 255)))) for i in range(n_s)], OBJECT_DTYPE)
+    for rot in ((0.0, float(PI32), 0.0), (0.21, float(PI32) + 0.4, 0.0)):
+        t = rtc.camera_params(598, 1080, (0.0, 0.0, 0.0), rot, 1.0 / 597)
+        s_plain = check_frame(ctx, oracle, tiny, t, RGB_PIXEL)
+        s_pack = check_frame(ctx, oracle, tiny, t, RGB_PIXEL, flags=FLAG_PACKET)
+        s_both = check_frame(ctx, oracle, tiny, t, RGB_PIXEL, flags=FLAG_PACKET | FLAG_CULL)
+        assert np.array_equal(s_plain, s_pack) and np.array_equal(s_plain, s_both)
+        assert len(s_plain) > 1080 + 20 * 597                               # (something is hit)
+    # full-size configs 3 and 4 (two sphere chunks): hit records and stream against the per-ray filter
+    for name in ("config3_4k_1024", "config4_8k_4096"):
+        objs = scenes.config_scene(name)
+        p = scenes.config_camera(name, frame=7) if name == "config4_8k_4096" else scenes.config_camera(name)
+        n_px = (p.x - 1) * p.y
+        ctx.set_objects(objs)
+        ctx.render(p, RGB_PIXEL, FLAG_KEEP_HITS)
+        d0, i0 = ctx.frame_hits(n_px)
+        s0 = np.array(ctx.frame_ansi())
+        for fl in (FLAG_PACKET, FLAG_PACKET | FLAG_CULL):
+            ctx.render(p, RGB_PIXEL, fl | FLAG_KEEP_HITS)
+            d1, i1 = ctx.frame_hits(n_px)
+            assert np.array_equal(i0, i1) and d0.tobytes() == d1.tobytes() and np.array_equal(s0, ctx.frame_ansi()), (name, fl)
+            ctx.render(p, RGB_PIXEL, fl)
+            assert np.array_equal(s0, ctx.frame_ansi()), (name, fl)
+
+
 def test_quantisers_exhaustive(ctx, oracle, rtc):
     """The integer quantisers over their whole domains: xterm-256 index of all 2^24 RGB values (shade kernel) and the
     NUL-padded decimal digits of all 256 byte values in every channel position (encoder), against the oracle (which

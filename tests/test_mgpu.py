@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from rtc_b200 import scenes
-from rtc_b200._types import (BIT_ASCII, BIT_PIXEL, FLAG_CULL, FLAG_SHADOWS, FLAG_UPDATE_REF_LAUNCH_LIMIT, MODE_NAMES,
+from rtc_b200._types import (BIT_ASCII, BIT_PIXEL, FLAG_CULL, FLAG_PACKET, FLAG_SHADOWS, FLAG_UPDATE_REF_LAUNCH_LIMIT, MODE_NAMES,
                              RGB_ASCII, RGB_NORMALS, RGB_PIXEL, SDL)
 from util import PI32
 
@@ -83,7 +83,7 @@ def test_mgpu_aligned_width_flags_and_scene_api(ctx, rtc, gather):
     with rtc.MultiGpu([0, 0, 0, 0], g) as m:
         m.set_objects(objs)
         for mode in (RGB_PIXEL, RGB_ASCII, BIT_ASCII, BIT_PIXEL):
-            for flags in (0, FLAG_CULL, FLAG_SHADOWS, FLAG_CULL | FLAG_SHADOWS):
+            for flags in (0, FLAG_CULL, FLAG_SHADOWS, FLAG_CULL | FLAG_SHADOWS, FLAG_PACKET, FLAG_PACKET | FLAG_CULL | FLAG_SHADOWS):
                 ctx.set_objects(objs)
                 want = np.array(ctx.update(p, mode, dt=0.0, flags=flags | FLAG_UPDATE_REF_LAUNCH_LIMIT))
                 got = m.update(p, mode, 0.0, flags | FLAG_UPDATE_REF_LAUNCH_LIMIT, copy=True)
