@@ -435,23 +435,42 @@ __device__ __forceinline__ f32x2 packet_flag(uint32_t fa, const PacketEnds& e)
     return add2(acc0, acc1);
 }
 
-// Two groups per NaN check (g1 < 0: one group).
+// A flagged group goes to the per-ray filter only if some lane that flagged it still has a ray the group could beat (the
+// group reject of resolve_candidates, applied before the 50 packed operations instead of after: three flagged groups in
+// four lie behind what their rays have already hit).
 template <int kThreads, int kRays>
-__device__ __forceinline__ void test_packet_groups(uint32_t fast_base, int g0, int g1, const PacketEnds& e, const RayOps<kRays>& ro,
-                                                   const int32_t* __restrict__ sphere_obj, int n_slots, int tid)
+__device__ __forceinline__ void packet_resolve(const Smem& s, uint32_t fa, int g, f32x2 f, const RayOps<kRays>& ro,
+                                               const int32_t* __restrict__ sphere_obj, int n_slots, int tid)
 {
-    const uint32_t fa0 = fast_base + 48u * (uint32_t)g0;
-    const f32x2 f0 = packet_flag(fa0, e);
-    f32x2 f1 = pack2(0.0f, 0.0f);
-    const uint32_t fa1 = fast_base + 48u * (uint32_t)(g1 < 0 ? g0 : g1);
-    if (g1 >= 0) f1 = packet_flag(fa1, e);
+    float lo, hi;
+    unpack2(f, lo, hi);
+    bool mine = !(lo == hi);                                     // NaN in either half (both are 0 otherwise)
+    if (mine) {
+        const float gd = s.gdmin[g];
+        float bmax = s.best_t[tid];
+#pragma unroll
+        for (int r = 1; r < kRays; ++r) bmax = fmaxf(bmax, s.best_t[r * kThreads + tid]);
+        mine = !(gd > bmax);
+    }
+    if (__any_sync(0xffffffffu, mine)) packet_slow_group<kThreads, kRays>(fa, g, ro, sphere_obj, n_slots, tid);
+}
+
+// N groups (gs[0 .. N)) per NaN check.
+template <int kThreads, int kRays, int N>
+__device__ __forceinline__ void test_packet_groups(const Smem& s, uint32_t fast_base, const int (&gs)[N], const PacketEnds& e,
+                                                   const RayOps<kRays>& ro, const int32_t* __restrict__ sphere_obj, int n_slots, int tid)
+{
+    f32x2 f[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) f[i] = packet_flag(fast_base + 48u * (uint32_t)gs[i], e);
+    f32x2 sum = f[0];
+#pragma unroll
+    for (int i = 1; i < N; ++i) sum = add2(sum, f[i]);
     float alo, ahi;
-    unpack2(add2(f0, f1), alo, ahi);
+    unpack2(sum, alo, ahi);
     if (__any_sync(0xffffffffu, !(alo == ahi))) {                // NaN somewhere (both halves are 0 otherwise)
-        unpack2(f0, alo, ahi);
-        if (__any_sync(0xffffffffu, !(alo == ahi))) packet_slow_group<kThreads, kRays>(fa0, g0, ro, sphere_obj, n_slots, tid);
-        unpack2(f1, alo, ahi);
-        if (g1 >= 0 && __any_sync(0xffffffffu, !(alo == ahi))) packet_slow_group<kThreads, kRays>(fa1, g1, ro, sphere_obj, n_slots, tid);
+#pragma unroll
+        for (int i = 0; i < N; ++i) packet_resolve<kThreads, kRays>(s, fast_base + 48u * (uint32_t)gs[i], gs[i], f[i], ro, sphere_obj, n_slots, tid);
     }
 }
 
@@ -586,9 +605,17 @@ trace_kernel(const FrameParams fp, const HoistBasis hb,
         }
         if (!CULL) {
             if (PACKET) {
+                int g = 0;
 #pragma unroll 1
-                for (int g = 0; g < n_groups; g += 2)
-                    test_packet_groups<kThreads, kRays>(fast_base, g, g + 1 < n_groups ? g + 1 : -1, pe, ro, sphere_obj, n_slots, tid);
+                for (; g + 4 <= n_groups; g += 4) {
+                    const int gs[4] = {g, g + 1, g + 2, g + 3};
+                    test_packet_groups<kThreads, kRays, 4>(s, fast_base, gs, pe, ro, sphere_obj, n_slots, tid);
+                }
+#pragma unroll 1
+                for (; g < n_groups; ++g) {
+                    const int gs[1] = {g};
+                    test_packet_groups<kThreads, kRays, 1>(s, fast_base, gs, pe, ro, sphere_obj, n_slots, tid);
+                }
             } else {
                 uint32_t fa = fast_base;
 #pragma unroll 2
@@ -643,9 +670,14 @@ trace_kernel(const FrameParams fp, const HoistBasis hb,
                     const int g0 = gb + __ffs(m) - 1;
                     m &= m - 1;
                     if (PACKET) {
-                        int g1 = -1;
-                        if (m) { g1 = gb + __ffs(m) - 1; m &= m - 1; }
-                        test_packet_groups<kThreads, kRays>(fast_base, g0, g1, pe, ro, sphere_obj, n_slots, tid);
+                        if (m) {
+                            const int gs[2] = {g0, gb + __ffs(m) - 1};
+                            m &= m - 1;
+                            test_packet_groups<kThreads, kRays, 2>(s, fast_base, gs, pe, ro, sphere_obj, n_slots, tid);
+                        } else {
+                            const int gs[1] = {g0};
+                            test_packet_groups<kThreads, kRays, 1>(s, fast_base, gs, pe, ro, sphere_obj, n_slots, tid);
+                        }
                         continue;
                     }
                     test_group<kThreads, AFFINE, kRays>(s, fast_base + 48u * (uint32_t)g0, g0, ex, ey, ez, sphere_obj, n_slots, tid);
