@@ -448,6 +448,20 @@ def test_packet_filter_is_invisible(ctx, oracle, rtc):
     inside = rtc.camera_params(161, 90, (3, -2, 5), (0.3, 1.0, 0), 1.0 / 160)
     check_frame(ctx, oracle, scenes.random_spheres(700, 34), inside, RGB_PIXEL, flags=FLAG_PACKET)
     check_frame(ctx, oracle, scenes.random_spheres(700, 34), inside, RGB_PIXEL, flags=FLAG_PACKET | FLAG_CULL | FLAG_SHADOWS)
+    # degenerate frames (a packet as tall as the frame: the deflation saturates and every sphere is a candidate), edge scenes,
+    # the reference's sphere capacity (21 chunks), a non-camera matrix (the flag is ignored: dot-product filter)
+    for (x, y) in ((2, 1), (3, 2), (18, 9), (38, 23)):
+        check_frame(ctx, oracle, scenes.default_scene(), rtc.camera_params(x, y, (0, 3, -10), (0.2, PI32, 0)), RGB_PIXEL, flags=FLAG_PACKET)
+    e = rtc.camera_params(64, 20, (0, 0, 0), (0, PI32, 0))
+    check_frame(ctx, oracle, np.zeros(0, OBJECT_DTYPE), e, RGB_PIXEL, flags=FLAG_PACKET)
+    check_frame(ctx, oracle, np.array([scenes.make_sphere((0, 0, 1), 50.0, (200, 20, 30))], OBJECT_DTYPE), e, RGB_PIXEL, flags=FLAG_PACKET)
+    check_frame(ctx, oracle, np.array([scenes.make_sphere((0, 0, 30), 5.0, (10, 200, 30)), scenes.make_sphere((0, 0, 30), 5.0, (200, 10, 30))],
+                                      OBJECT_DTYPE), e, RGB_PIXEL, flags=FLAG_PACKET)
+    check_frame(ctx, oracle, scenes.random_spheres(52083, 41), rtc.camera_params(34, 9, (0, 0, -120), (0, PI32, 0), 1.0 / 33), RGB_PIXEL,
+                flags=FLAG_PACKET | FLAG_CULL)
+    skew = rtc.camera_params(161, 90, (0, 0, -120), (0, PI32, 0), 1.0 / 160)
+    skew.inv_view[1] = 0.3                                                    # 3x3 no longer orthonormal
+    check_frame(ctx, oracle, scenes.random_spheres(300, 35), skew, RGB_PIXEL, flags=FLAG_PACKET)
     # sub-pixel to few-pixel spheres all over a tall frame (a pixel is 1.07e-3 rad high; radii 2e-4 .. 4e-3 rad), rolled and
     # pitched camera, ragged width: many of them lie strictly between the end rays of a packet
     rng = np.random.default_rng(11)
