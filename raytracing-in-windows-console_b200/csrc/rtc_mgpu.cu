@@ -3,7 +3,7 @@
 // The reference's frame driver (RayTracingManager.cu:76-154) can only ever use one GPU.  Here the frame shards by rows:
 // pixels are independent given the replicated scene (<= 0.26 MB) and the 96-byte camera block, so device g traces rows
 // [rows[g], rows[g+1]) with no data-path collective.  One worker thread and one stream per device (a CUDA launch costs
-// 2-4 us of host time; five launches x eight devices from one thread would be most of a 0.2 ms frame), frames pipelined
+// 2-4 us of host time; three launches x eight devices from one thread would be most of a 0.17 ms frame), frames pipelined
 // kSlots deep, no Python, no process boundary, no shared-memory polling between processes.
 //
 // Two ways from bands to one frame (rtc_mgpu_create's `gather`):

@@ -47,12 +47,17 @@ def check(y, W, e1, e2, n_pk=20000, n_sph=400, kr=8, tiny=False, coeff=1.5, base
     return viol
 
 
-bad = 0
-for args in ((2160, 3840, 0.325, 0.577), (1080, 1920, 0.325, 0.577), (150, 399, 0.866, 0.577), (4320, 7680, 0.325, 0.577), (2160, 3840, 3.0, 5.0)):
-    for tiny in (False, True):
-        bad += check(*args, tiny=tiny)
-        bad += check(*args, tiny=tiny, kr=4)
-print("violations with the shipped bound:", bad)
-print("slack: spheres centred between rows 3 and 4 of a packet, E = eps0 + coeff * D^2")
-for coeff in (0.0, 0.05, 0.1, 0.2, 0.5):
-    check(2160, 3840, 0.325, 0.577, n_pk=20000, n_sph=2000, tiny=True, coeff=coeff, base=2.7e-6)
+def main():
+    bad = 0
+    for args in ((2160, 3840, 0.325, 0.577), (1080, 1920, 0.325, 0.577), (150, 399, 0.866, 0.577), (4320, 7680, 0.325, 0.577), (2160, 3840, 3.0, 5.0)):
+        for tiny in (False, True):
+            bad += check(*args, tiny=tiny)
+            bad += check(*args, tiny=tiny, kr=4)
+    print("violations with the shipped bound:", bad)
+    print("slack: spheres centred between rows 3 and 4 of a packet, E = eps0 + coeff * D^2")
+    for coeff in (0.0, 0.05, 0.1, 0.2, 0.5):
+        check(2160, 3840, 0.325, 0.577, n_pk=20000, n_sph=2000, tiny=True, coeff=coeff, base=2.7e-6)
+
+
+if __name__ == "__main__":
+    main()
