@@ -23,6 +23,23 @@ def test_header_symbols_exported(rtc):
     assert sorted(rtc.EXPORTS) == syms               # the Python binding tracks the header
 
 
+def test_header_constants_match_binding(rtc):
+    """Flag, mode and gather values of the Python binding == include/rtc.h."""
+    src = open(os.path.join(ROOT, "include", "rtc.h")).read()
+    flags = {m.group(1): 1 << int(m.group(2)) for m in re.finditer(r"RTC_FLAG_(\w+)\s*=\s*1u\s*<<\s*(\d+)", src)}
+    assert len(flags) >= 6
+    for name, value in flags.items():
+        assert getattr(rtc, "FLAG_" + name) == value, name
+    assert len(set(flags.values())) == len(flags)
+    modes = re.search(r"typedef enum rtc_mode \{(.*?)\}", src, re.S).group(1)
+    values = dict(re.findall(r"RTC_([A-Z_0-9]+)\s*=\s*(\d+)", modes))
+    assert sorted(values) == ["BIT_ASCII", "BIT_PIXEL", "RGB_ASCII", "RGB_NORMALS", "RGB_PIXEL", "SDL"]
+    for name, value in values.items():
+        assert getattr(rtc, name) == int(value), name
+    for name in ("GATHER_HOST", "GATHER_P2P"):
+        assert getattr(rtc, name) == int(re.search(r"RTC_%s\s*=\s*(\d+)" % name, src).group(1))
+
+
 def test_pod_layouts(rtc):
     import ctypes
     assert ctypes.sizeof(rtc.RtcParams) == 96
