@@ -81,7 +81,7 @@ def test_facade_inner_seam_raw_cells(oracle, tmp_path):
     build_facade()
     subprocess.check_call([os.path.join(HOST, "facade_test"), str(tmp_path), "raw"])
     p = scenes.config_camera("config1_240x64")
-    objs = oracle.update_objects(scenes.default_scene(), 0.0) if False else scenes.default_scene()   # RayTrace runs no physics step
+    objs = scenes.default_scene()                                       # RayTracing::RayTrace runs no physics step
     for mode in range(6):
         got = np.fromfile(tmp_path / f"raw_240x64_m{mode}.bin", np.uint8)
         want = oracle.trace_raw(objs, p, mode)
