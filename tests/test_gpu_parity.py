@@ -13,7 +13,7 @@ import pytest
 from rtc_b200 import scenes
 from rtc_b200._types import (BIT_ASCII, BIT_PIXEL, FLAG_CULL, FLAG_KEEP_HITS, FLAG_SHADOWS, FLAG_UPDATE_REF_LAUNCH_LIMIT, MODE_NAMES,
                              OBJECT_DTYPE, RGB_ASCII, RGB_NORMALS, RGB_PIXEL, SDL, mode_bpp, mode_cell, mode_has_glyph)
-from util import PI32, bind_stream, objs_from_bytes, params_from_bytes, parse_stream, unbind_stream
+from util import PI32, bind_stream, objs_from_bytes, params_from_bytes, unbind_stream
 
 pytestmark = pytest.mark.gpu
 
