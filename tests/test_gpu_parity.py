@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from rtc_b200 import scenes
-from rtc_b200._types import (BIT_ASCII, BIT_PIXEL, FLAG_CULL, FLAG_KEEP_HITS, FLAG_SHADOWS, FLAG_UPDATE_REF_LAUNCH_LIMIT, MODE_NAMES,
+from rtc_b200._types import (BIT_ASCII, BIT_PIXEL, FLAG_CULL, FLAG_KEEP_HITS, FLAG_PACKET, FLAG_SHADOWS, FLAG_UPDATE_REF_LAUNCH_LIMIT, MODE_NAMES,
                              OBJECT_DTYPE, RGB_ASCII, RGB_NORMALS, RGB_PIXEL, SDL, mode_bpp, mode_cell, mode_has_glyph)
 from util import PI32, bind_stream, objs_from_bytes, params_from_bytes, unbind_stream
 
@@ -429,7 +429,6 @@ def test_packet_filter_is_invisible(ctx, oracle, rtc):
     ray) must not change a hit record, colour or stream byte: whole frames against the oracle, alone and with culling /
     shadow rays, 8-ray and 4-ray packets (console-sized frames), chunked sphere lists, camera inside the cloud, and --
     the case the chord bound exists for -- spheres much smaller than a packet, sitting between its end rays."""
-    from rtc_b200._types import FLAG_PACKET
     objs = scenes.config_scene("config2_1080p_64")
     p = scenes.config_camera("config2_1080p_64")
     check_frame(ctx, oracle, objs, p, RGB_PIXEL, flags=FLAG_PACKET)
@@ -527,7 +526,7 @@ def test_quantisers_exhaustive(ctx, oracle, rtc):
 def test_random_scenes_sweep(ctx, oracle, rtc):
     """Seeded sweep of small frames: random sphere clouds (radius 0 included, overlapping and nested spheres), planes
     of either facing, cameras outside / inside the cloud / inside a sphere, arbitrary rotations and pixel aspects,
-    every flag combination -- hit records bit-exact, colours and stream as in check_frame."""
+    every flag combination (each also with the packet filter) -- hit records bit-exact, colours and stream as in check_frame."""
     rng = np.random.default_rng(2024)
     for case in range(72):
         n = int(rng.integers(1, 400))
@@ -553,6 +552,7 @@ def test_random_scenes_sweep(ctx, oracle, rtc):
         mode = [RGB_PIXEL, RGB_ASCII, BIT_PIXEL, BIT_ASCII, RGB_NORMALS][case % 5]
         flags = [0, FLAG_CULL, FLAG_SHADOWS, FLAG_CULL | FLAG_SHADOWS][case % 4]
         check_frame(ctx, oracle, objs, p, mode, flags=flags)
+        check_frame(ctx, oracle, objs, p, mode, flags=flags | FLAG_PACKET)
 
 
 def test_encoder_state_survives_skipped_launches(ctx, oracle, rtc):
